@@ -1,0 +1,319 @@
+"""Op surface of the reference on top of libsigma_b200 (no torch arithmetic on these paths).
+
+`selective_scan_cuda_core_fwd/bwd` have the exact pybind signatures of the reference extension
+(csrc/selective_scan/selective_scan.cpp:364-367); `sigma_b200/dropin/selective_scan_cuda_core.py`
+re-exports them under the reference's module name.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPE = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("sigma_b200 ops run on CUDA tensors only (there is no CPU path)")
+
+
+def selective_scan_cuda_core_fwd(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1,
+                                 _force_split=0):
+    """Drop-in for selective_scan_cuda_core.fwd (selective_scan.cpp:165-249) -> [out, x]."""
+    _require_cuda(u, delta, A, B, C, D, delta_bias)
+    if u.dtype not in _DTYPE:
+        raise RuntimeError(f"selective_scan fwd: unsupported dtype {u.dtype}")
+    if not (delta.dtype == u.dtype and B.dtype == u.dtype and C.dtype == u.dtype):
+        raise RuntimeError("selective_scan fwd: u, delta, B, C must share one dtype (selective_scan.cpp:177-180)")
+    if A.dtype != torch.float32 or (D is not None and D.dtype != torch.float32) or \
+            (delta_bias is not None and delta_bias.dtype != torch.float32):
+        raise RuntimeError("selective_scan fwd: A, D, delta_bias must be float32 (selective_scan.cpp:176,211,219)")
+    if u.dim() != 3 or delta.shape != u.shape or B.dim() != 4 or C.shape != B.shape:
+        raise RuntimeError("selective_scan fwd: expected u,delta (B,D,L) and B,C (B,G,N,L)")
+    for t, n in ((u, "u"), (delta, "delta"), (B, "B"), (C, "C")):
+        if t.stride(-1) != 1 and t.size(-1) != 1:
+            raise RuntimeError(f"selective_scan fwd: {n} must have unit stride along seqlen (selective_scan.cpp:191-194)")
+    batch, dim, L = u.shape
+    G, N = B.shape[1], B.shape[2]
+    if A.shape != (dim, N) or B.shape[0] != batch or B.shape[3] != L:
+        raise RuntimeError("selective_scan fwd: shape mismatch")
+    if dim % (G * nrows) != 0:
+        raise RuntimeError(f"selective_scan fwd: dim={dim} must be divisible by ngroups*nrows={G * nrows}")
+    if N > 256 // nrows:
+        raise RuntimeError("selective_scan fwd: dstate too large (selective_scan.cpp:198)")
+    if D is not None:
+        D = D.contiguous()
+    if delta_bias is not None:
+        delta_bias = delta_bias.contiguous()
+    out = torch.empty_like(delta)
+    if out.stride(-1) != 1:
+        out = torch.empty(delta.shape, dtype=delta.dtype, device=delta.device)
+    nchunks = (L + 2047) // 2048
+    x = torch.empty((batch, dim, nchunks, 2 * N), dtype=torch.float32, device=u.device)
+    st = _lib.ScanStrides(u.stride(0), u.stride(1), delta.stride(0), delta.stride(1), A.stride(0), A.stride(1),
+                          B.stride(0), B.stride(1), B.stride(2), C.stride(0), C.stride(1), C.stride(2),
+                          out.stride(0), out.stride(1))
+    L_ = _lib.lib()
+    dt = _DTYPE[u.dtype]
+    wsb = L_.sigma_scan_fwd_workspace_bytes(batch, dim, L, N, G, dt)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=u.device)
+    if _force_split and dt == _lib.F32:
+        rc = L_.sigma_scan_fwd_f32_split(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias),
+                                         _ptr(out), _ptr(x), batch, dim, L, N, G, int(bool(delta_softplus)),
+                                         ctypes.byref(st), _ptr(ws), wsb, int(_force_split), _stream())
+    else:
+        rc = L_.sigma_scan_fwd(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias),
+                               _ptr(out), _ptr(x), batch, dim, L, N, G, dt, int(bool(delta_softplus)),
+                               ctypes.byref(st), _ptr(ws), wsb, _stream())
+    _lib.check(rc, "sigma_scan_fwd")
+    return [out, x]
+
+
+def selective_scan_cuda_core_bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, nrows=1):
+    """Drop-in for selective_scan_cuda_core.bwd (selective_scan.cpp:251-362)
+    -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]."""
+    _require_cuda(u, delta, A, B, C, D, delta_bias, dout)
+    if u.dtype not in _DTYPE:
+        raise RuntimeError(f"selective_scan bwd: unsupported dtype {u.dtype}")
+    batch, dim, L = u.shape
+    G, N = B.shape[1], B.shape[2]
+    u, delta, B, C, dout = (t.contiguous() for t in (u, delta, B, C, dout))
+    A = A.contiguous()
+    D = D.contiguous() if D is not None else None
+    delta_bias = delta_bias.contiguous() if delta_bias is not None else None
+    du, ddelta = torch.empty_like(u), torch.empty_like(delta)
+    dA = torch.empty((dim, N), dtype=torch.float32, device=u.device)
+    dB = torch.empty((batch, G, N, L), dtype=torch.float32, device=u.device)
+    dC = torch.empty((batch, G, N, L), dtype=torch.float32, device=u.device)
+    dD = torch.empty(dim, dtype=torch.float32, device=u.device) if D is not None else None
+    dbias = torch.empty(dim, dtype=torch.float32, device=u.device) if delta_bias is not None else None
+    L_ = _lib.lib()
+    dt = _DTYPE[u.dtype]
+    wsb = L_.sigma_scan_bwd_workspace_bytes(batch, dim, L, N, G, dt)
+    ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
+    rc = L_.sigma_scan_bwd(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias), _ptr(dout),
+                           _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias),
+                           batch, dim, L, N, G, dt, int(bool(delta_softplus)), _ptr(ws), wsb, _stream())
+    _lib.check(rc, "sigma_scan_bwd")
+    # the reference returns dB/dC cast to the input dtype (selective_scan.cpp:360)
+    return [du, ddelta, dA, dB.to(u.dtype), dC.to(u.dtype), dD, dbias]
+
+
+class SelectiveScan(torch.autograd.Function):
+    """vmamba.py:34-78 — fp32 cast under AMP, contiguity fix-ups, 3-D B/C unsqueeze; backward with nrows=1."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1):
+        assert nrows in (1, 2, 3, 4), f"{nrows}"
+        assert u.shape[1] % (B.shape[1] * nrows) == 0, f"{nrows}, {u.shape}, {B.shape}"
+        ctx.delta_softplus, ctx.nrows = delta_softplus, nrows
+        u, delta, B, C = (t if t.stride(-1) == 1 else t.contiguous() for t in (u, delta, B, C))
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        out, x = selective_scan_cuda_core_fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, nrows)
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        du, ddelta, dA, dB, dC, dD, dbias = selective_scan_cuda_core_bwd(
+            u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+        dB = dB.squeeze(1) if ctx.squeeze_B else dB
+        dC = dC.squeeze(1) if ctx.squeeze_C else dC
+        return du, ddelta, dA, dB, dC, dD, dbias, None, None
+
+
+class SelectiveScanFn(torch.autograd.Function):
+    """selective_scan_interface.py:10-75 (no AMP cast: dtype follows the input, D/bias promoted to fp32)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1):
+        u, delta, B, C = (t if t.stride(-1) == 1 else t.contiguous() for t in (u, delta, B, C))
+        ctx.squeeze_B = B.dim() == 3
+        ctx.squeeze_C = C.dim() == 3
+        if ctx.squeeze_B:
+            B = B.unsqueeze(1)
+        if ctx.squeeze_C:
+            C = C.unsqueeze(1)
+        ctx.d_dtype = D.dtype if D is not None else None
+        ctx.bias_dtype = delta_bias.dtype if delta_bias is not None else None
+        D = D.float() if D is not None else None
+        delta_bias = delta_bias.float() if delta_bias is not None else None
+        assert u.shape[1] % (B.shape[1] * nrows) == 0
+        assert nrows in (1, 2, 3, 4)
+        out, x = selective_scan_cuda_core_fwd(u, delta, A, B, C, D, delta_bias, delta_softplus, nrows)
+        ctx.delta_softplus, ctx.nrows = delta_softplus, nrows
+        ctx.save_for_backward(u, delta, A, B, C, D, delta_bias, x)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *args):
+        u, delta, A, B, C, D, delta_bias, x = ctx.saved_tensors
+        du, ddelta, dA, dB, dC, dD, dbias = selective_scan_cuda_core_bwd(
+            u, delta, A, B, C, D, delta_bias, dout, x, ctx.delta_softplus, 1)
+        dB = dB.squeeze(1) if ctx.squeeze_B else dB
+        dC = dC.squeeze(1) if ctx.squeeze_C else dC
+        dD = dD.to(ctx.d_dtype) if dD is not None else None
+        dbias = dbias.to(ctx.bias_dtype) if dbias is not None else None
+        return du, ddelta, dA, dB, dC, dD, dbias, None, None
+
+
+def selective_scan_fn(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False, nrows=1):
+    """selective_scan_interface.py:78-83."""
+    return SelectiveScanFn.apply(u, delta, A, B, C, D, delta_bias, delta_softplus, nrows)
+
+
+# ---- direction maps (pure index shuffles; the fused inference path never materialises them) ----
+class CrossScan(torch.autograd.Function):
+    """vmamba.py:80-98.  (B,C,H,W) -> (B,4,C,L): row-major, column-major, and both reversed."""
+
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        ctx.shape = (B, C, H, W)
+        xs = x.new_empty((B, 4, C, H * W))
+        xs[:, 0] = x.flatten(2, 3)
+        xs[:, 1] = x.transpose(2, 3).flatten(2, 3)
+        xs[:, 2:4] = xs[:, 0:2].flip(-1)
+        return xs
+
+    @staticmethod
+    def backward(ctx, ys):
+        B, C, H, W = ctx.shape
+        return _merge4(ys, H, W).view(B, C, H, W)
+
+
+def _merge4(ys, H, W):
+    B, K, D, L = ys.shape
+    ys = ys[:, 0:2] + ys[:, 2:4].flip(-1)
+    return ys[:, 0] + ys[:, 1].reshape(B, D, W, H).transpose(2, 3).reshape(B, D, L)
+
+
+def _scan4(x, H, W):
+    B, C, L = x.shape
+    xs = x.new_empty((B, 4, C, L))
+    xs[:, 0] = x
+    xs[:, 1] = x.view(B, C, H, W).transpose(2, 3).flatten(2, 3)
+    xs[:, 2:4] = xs[:, 0:2].flip(-1)
+    return xs
+
+
+class CrossMerge(torch.autograd.Function):
+    """vmamba.py:100-121.  (B,4,D,H,W) -> (B,D,L)."""
+
+    @staticmethod
+    def forward(ctx, ys):
+        B, K, D, H, W = ys.shape
+        ctx.shape = (H, W)
+        return _merge4(ys.view(B, K, D, -1), H, W)
+
+    @staticmethod
+    def backward(ctx, x):
+        H, W = ctx.shape
+        B, C, L = x.shape
+        return _scan4(x, H, W).view(B, 4, C, H, W)
+
+
+class CrossScan_multimodal(torch.autograd.Function):
+    """vmamba.py:123-141.  two (B,C,H,W) -> (B,2,C,2L): [rgb ‖ x] and its reverse."""
+
+    @staticmethod
+    def forward(ctx, x_rgb, x_e):
+        B, C, H, W = x_rgb.shape
+        ctx.shape = (B, C, H, W)
+        xs = x_rgb.new_empty((B, 2, C, 2 * H * W))
+        xs[:, 0, :, :H * W] = x_rgb.flatten(2, 3)
+        xs[:, 0, :, H * W:] = x_e.flatten(2, 3)
+        xs[:, 1] = xs[:, 0].flip(-1)
+        return xs
+
+    @staticmethod
+    def backward(ctx, ys):
+        B, C, H, W = ctx.shape
+        y = ys[:, 0] + ys[:, 1].flip(-1)
+        return y[:, :, :H * W].reshape(B, C, H, W), y[:, :, H * W:].reshape(B, C, H, W)
+
+
+class CrossMerge_multimodal(torch.autograd.Function):
+    """vmamba.py:143-163.  (B,2,D,2L) -> two (B,D,L)."""
+
+    @staticmethod
+    def forward(ctx, ys):
+        B, K, D, L2 = ys.shape
+        y = ys[:, 0] + ys[:, 1].flip(-1)
+        return y[:, :, :L2 // 2], y[:, :, L2 // 2:]
+
+    @staticmethod
+    def backward(ctx, x1, x2):
+        B, C, L = x1.shape
+        xs = x1.new_empty((B, 2, C, 2 * L))
+        xs[:, 0, :, :L] = x1
+        xs[:, 0, :, L:] = x2
+        xs[:, 1] = xs[:, 0].flip(-1)
+        return xs
+
+
+def _pick_nrows(D, nrows):
+    if nrows >= 1:
+        return nrows
+    return 4 if D % 4 == 0 else 3 if D % 3 == 0 else 2 if D % 2 == 0 else 1
+
+
+def _scan_core(xs, x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds, nrows, delta_softplus):
+    """x_proj / dt_proj einsums + SelectiveScan, shared by the two composed paths (vmamba.py:195-215, 401-421)."""
+    B, K, D, L = xs.shape
+    R, N = dt_projs_weight.shape[2], A_logs.shape[1]
+    x_dbl = torch.einsum("bkdl,kcd->bkcl", xs, x_proj_weight)
+    if x_proj_bias is not None:
+        x_dbl = x_dbl + x_proj_bias.view(1, K, -1, 1)
+    dts, Bs, Cs = torch.split(x_dbl, [R, N, N], dim=2)
+    dts = torch.einsum("bkrl,kdr->bkdl", dts, dt_projs_weight)
+    ys = SelectiveScan.apply(xs.reshape(B, K * D, L).float(), dts.reshape(B, K * D, L).float(),
+                             -torch.exp(A_logs.float()), Bs.float().contiguous(), Cs.float().contiguous(),
+                             Ds.float(), dt_projs_bias.reshape(-1).float(), delta_softplus, nrows)
+    return ys.view(B, K, D, L)
+
+
+def cross_selective_scan(x, x_proj_weight=None, x_proj_bias=None, dt_projs_weight=None, dt_projs_bias=None,
+                         A_logs=None, Ds=None, out_norm=None, softmax_version=False, nrows=-1, delta_softplus=True):
+    """vmamba.py:165-226 (composed path: used when autograd is recording)."""
+    B, D, H, W = x.shape
+    nrows = _pick_nrows(D, nrows)
+    ys = _scan_core(CrossScan.apply(x), x_proj_weight, x_proj_bias, dt_projs_weight, dt_projs_bias, A_logs, Ds,
+                    nrows, delta_softplus)
+    y = CrossMerge.apply(ys.view(B, 4, D, H, W))
+    y = y.transpose(1, 2).contiguous().view(B, H, W, D)
+    if softmax_version:
+        return y.softmax(dim=-1).to(x.dtype)
+    return out_norm(y).to(x.dtype)
+
+
+def cross_selective_scan_multimodal_k2(x_rgb, x_e, x_proj_weight=None, x_proj_bias=None, dt_projs_weight=None,
+                                       dt_projs_bias=None, A_logs=None, Ds=None, out_norm1=None, out_norm2=None,
+                                       softmax_version=False, nrows=-1, delta_softplus=True):
+    """vmamba.py:369-430 (composed path)."""
+    B, D, H, W = x_rgb.shape
+    nrows = _pick_nrows(D, nrows)
+    ys = _scan_core(CrossScan_multimodal.apply(x_rgb, x_e), x_proj_weight, x_proj_bias, dt_projs_weight,
+                    dt_projs_bias, A_logs, Ds, nrows, delta_softplus)
+    y_r, y_e = CrossMerge_multimodal.apply(ys)
+    y_r = y_r.transpose(1, 2).contiguous().view(B, H, W, D)
+    y_e = y_e.transpose(1, 2).contiguous().view(B, H, W, D)
+    return out_norm1(y_r).to(x_rgb.dtype), out_norm2(y_e).to(x_e.dtype)

@@ -30,10 +30,31 @@ def save(name, **arrays):
     print("wrote", name, {k: v.shape for k, v in out.items()})
 
 
+def bwd_goldens(ns):
+    """Gradients of the reference's selective_scan_ref by torch autograd — exactly what the
+    reference's own test compares its CUDA bwd against (test_selective_scan.py:181-224)."""
+    for idx, (b, d, n, L, g, has_D, has_b, sp) in enumerate([
+        (2, 24, 8, 200, 2, True, True, True), (1, 16, 16, 333, 1, True, True, True),
+        (2, 12, 4, 97, 3, False, False, False), (1, 8, 4, 2500, 1, True, True, True),
+    ]):
+        u, dl, A, Bm, Cm, D, bias = P.scan_inputs(SEED + 1, b, d, n, L, g, has_D=has_D, has_bias=has_b)
+        dout = P.randn(SEED + 1, f"bwd/dout{idx}", (b, d, L))
+        leaves = [t.clone().requires_grad_(True) if t is not None else None for t in (u, dl, A, Bm, Cm, D, bias)]
+        with torch.enable_grad():
+            out = ns.selective_scan_ref(*leaves, sp)
+            out.backward(dout)
+        names = ["du", "ddelta", "dA", "dB", "dC", "dD", "dbias"]
+        save(f"scan_bwd_case{idx}", cfg=np.array((b, d, n, L, g, int(has_D), int(has_b), int(sp))),
+             out=out.detach(), **{nm: t.grad for nm, t in zip(names, leaves) if t is not None})
+
+
 @torch.no_grad()
 def main():
     torch.set_num_threads(8)
     ns = ref_shim.install()
+    bwd_goldens(ns)
+    if "--only-bwd" in sys.argv:
+        return
     vm, dv, md, bd = ns.vmamba, ns.dual_vmamba, ns.mamba_decoder, ns.builder
 
     # ---------------- op level: selective scan ----------------
