@@ -55,9 +55,33 @@ class DropPath(nn.Module):
         return f"drop_prob={self.drop_prob}"
 
 
+_FORCE_COMPOSED = False
+
+
+class composed_path:
+    """Context manager: run the reference's op composition (the training path) even under no_grad.
+    Used by the parity tests to check both paths against the same goldens."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global _FORCE_COMPOSED
+        self.prev, _FORCE_COMPOSED = _FORCE_COMPOSED, self.on
+
+    def __exit__(self, *a):
+        global _FORCE_COMPOSED
+        _FORCE_COMPOSED = self.prev
+
+
 def _fused_ok(*tensors):
     """The fused inference path is taken whenever autograd is not recording."""
-    return (not torch.is_grad_enabled()) and all(t.is_cuda and t.dtype == torch.float32 for t in tensors)
+    if _FORCE_COMPOSED or torch.is_grad_enabled():
+        return False
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("sigma_b200 modules run on CUDA tensors only (there is no CPU path)")
+    return all(t.dtype == torch.float32 for t in tensors)
 
 
 # --------------------------------------------------------------------------------------------
