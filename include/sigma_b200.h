@@ -72,24 +72,6 @@ int sigma_scan_fwd(const void *u, const void *delta, const float *A, const void 
                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
- * a3. backward of a1.
- * Replaces `selective_scan_cuda_core.bwd(u, delta, A, B, C, D, delta_bias, dout, x,
- * delta_softplus, nrows) -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]`
- * (selective_scan.cpp:251-362, selective_scan_bwd_kernel.cuh:68-274).
- * All tensors contiguous.  du, ddelta: (batch, dim, seqlen) in `dtype`; dA (dim, dstate),
- * dD, ddelta_bias (dim) fp32 — OVERWRITTEN (not accumulated); dB, dC (batch, ngroups, dstate,
- * seqlen) fp32, overwritten.  dD / ddelta_bias may be NULL when D / delta_bias are NULL.
- * ------------------------------------------------------------------------------------------ */
-size_t sigma_scan_bwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype);
-
-int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void *B, const void *C,
-                   const float *D, const float *delta_bias, const void *dout,
-                   void *du, void *ddelta, float *dA, float *dB, float *dC, float *dD,
-                   float *ddelta_bias,
-                   int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
-                   int delta_softplus, void *workspace, size_t workspace_bytes, void *stream);
-
-/* ------------------------------------------------------------------------------------------
  * a4+a5 (+a8/a9 cores). Fused multi-direction SS2D scan, channels-last.
  * Replaces, in one launch, CrossScan (vmamba.py:80-98) + the dt_proj einsum (vmamba.py:199) +
  * delta_bias/softplus + SelectiveScan (vmamba.py:213) + the un-flip / un-transpose half of
@@ -98,19 +80,20 @@ int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void 
  * and with kind=SIGMA_DIRS_CROSS the two C-swapped scans of Cross_Mamba_Attention_SSM.forward
  * (vmamba.py:1528-1539).
  *
- *   xc    (batch, Lseq, D)          fp32, channels-last: the dwconv+SiLU output (Lseq = H·W, or
- *                                   2·H·W for SEQ2 = [rgb ‖ x] per image, or H·W per modality m
- *                                   with batch index = 2·b+m for CROSS)
- *   xdbl  (batch, Lseq, K, Cp)      fp32: x_proj output per POSITION and direction, row k =
- *                                   [dt_r (R) | B (N) | C (N) | pad], Cp % 4 == 0
+ *   xc    (batch, Lseq, D)          fp32, channels-last: the dwconv+SiLU output.  Lseq = H·W; for
+ *                                   SEQ2 Lseq = 2·H·W = [rgb ‖ x] per image; for CROSS batch = 2·images,
+ *                                   modality-major: [0, batch/2) rgb, [batch/2, batch) modal-x
+ *   xdbl  (batch, Lseq, K, Cp)      fp32: x_proj output per POSITION and direction (K = 4 / 2 / 1), row =
+ *                                   [B (N) | C (N) | dt_r (R) | 0-pad], Cp = sigma_ss2d_padded_cp(N, R)
  *   y     (K, batch, Lseq, D)       fp32: direction k's output stored at the POSITION it belongs
  *                                   to (so CrossMerge is a plain sum over k)
- *   dtw (K, D, R), dtb (K, D), A (K·D, N) [= -exp(A_logs)], Ds (K·D)
+ *   dtw (Kw, D, R), dtb (Kw, D), A (Kw·D, N) [= -exp(A_logs)], Ds (Kw·D); Kw = K, or 2 (modalities) for CROSS
  * ------------------------------------------------------------------------------------------ */
 #define SIGMA_DIRS_CROSS4 0 /* K=4: row-major, column-major, and both reversed (vmamba.py:86-88) */
 #define SIGMA_DIRS_SEQ2 1   /* K=2: forward and reversed over a flat sequence (vmamba.py:130-131) */
 #define SIGMA_DIRS_CROSS 2  /* K=1 per modality, C taken from the other modality (vmamba.py:1530,1536) */
 
+int sigma_ss2d_padded_cp(int N, int R); /* row length of xdbl, or -1 if R > 64 */
 size_t sigma_ss2d_scan_workspace_bytes(int kind, int batch, int H, int W, int D, int N);
 
 int sigma_ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw,
@@ -119,36 +102,29 @@ int sigma_ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const floa
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
- * Row-wise / elementwise pieces of a5-a11 (channels-last, fp32).
+ * Row-wise / stencil pieces of a5-a11 (channels-last, fp32; D % 4 == 0, 16-byte aligned rows).
  * ------------------------------------------------------------------------------------------ */
 /* nn.LayerNorm over the last dim (vmamba.py:1693,724,2173; eps=1e-5): y = (x-mean)/sqrt(var+eps)·w+b */
 int sigma_layernorm_fwd(const float *x, const float *w, const float *b, float *y, int64_t rows,
                         int C, float eps, void *stream);
 
 /* depthwise 3x3 conv (pad 1) + bias + SiLU, channels-last (vmamba.py:683-692,1072).
- * x rows have stride x_row_stride floats (so the x half of in_proj's output is read in place);
- * w is the nn.Conv2d weight (D,1,3,3) contiguous; y (batch,H,W,D) contiguous.            */
-int sigma_dwconv3x3_silu_fwd(const float *x, int64_t x_row_stride, const float *w,
-                             const float *bias, float *y, int batch, int H, int W, int D,
-                             void *stream);
+ * x: position rows x_row_stride floats apart, images x_batch_stride apart (so the x half of
+ * in_proj's (.., 2D) output is read in place); w is the nn.Conv2d weight (D,1,3,3) contiguous;
+ * y: (H·W, D) rows per image, images y_batch_stride floats apart.                         */
+int sigma_dwconv3x3_silu_fwd(const float *x, int64_t x_row_stride, int64_t x_batch_stride,
+                             const float *w, const float *bias, float *y, int64_t y_batch_stride,
+                             int batch, int H, int W, int D, void *stream);
 
-/* CrossMerge sum + out_norm LayerNorm + gate (vmamba.py:217-224,1077):
- *   yo[r,:] = LN(Σ_k y[k,r,:])·gamma+beta  ·  (z ? SiLU(z[r,:]) : 1)  ·  (gate ? gate[r / rows_per_gate, :] : 1)
- * z rows have stride z_row_stride (the z half of in_proj's output, read in place).           */
-int sigma_merge_norm_gate_fwd(const float *y, int K, int64_t k_stride, const float *gamma,
-                              const float *beta, const float *z, int64_t z_row_stride,
-                              const float *gate, int64_t rows_per_gate, float *yo,
-                              int64_t yo_row_stride, int64_t rows, int D, float eps, void *stream);
-
-/* ------------------------------------------------------------------------------------------
- * Dense projections (in_proj / x_proj / out_proj / PatchMerging / PatchExpand linears,
- * vmamba.py:679,725,616,195; MambaDecoder.py:17,39,82-83): tcgen05 (5th-gen tensor core) TF32
- * GEMM, fp32 accumulate in TMEM, TMA-fed:  C[M,N] = A[M,K]·W[N,K]^T (+ bias[N]) (+ residual[M,N]).
- * A rows: lda floats apart (lda % 4 == 0), W (N,K) contiguous, K % 4 == 0; C rows ldc apart.
- * ------------------------------------------------------------------------------------------ */
-int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *bias,
-                      const float *residual, int64_t ldr, float *C, int64_t ldc, int64_t M, int N,
-                      int K, void *stream);
+/* CrossMerge sum + out_norm LayerNorm + gates (vmamba.py:217-224,1077; ConMB: 423-428,1280-1281):
+ *   out[r,:] = (LN(Σ_k y[k][r,:])·gamma+beta) · (z ? SiLU(z[r,:]) : 1) · (gate ? gate[r / rows_per_batch, :] : 1)
+ * Row r = (b, i) with b = r / rows_per_batch: input row at y + k·k_stride + b·in_batch_stride + i·D,
+ * output row at out + b·out_batch_stride + i·out_row_stride, z row at z + r·z_row_stride.     */
+int sigma_merge_norm_gate_fwd(const float *y, int K, int64_t k_stride, int64_t in_batch_stride,
+                              const float *gamma, const float *beta, const float *z,
+                              int64_t z_row_stride, const float *gate, float *out,
+                              int64_t out_batch_stride, int64_t out_row_stride, int64_t rows,
+                              int64_t rows_per_batch, int D, float eps, void *stream);
 
 #ifdef __cplusplus
 }

@@ -187,3 +187,106 @@ int sigma_scan_fwd_f32_split(const float *u, const float *delta, const float *A,
 
 #pragma GCC visibility pop
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// fused channels-last pipeline
+// ---------------------------------------------------------------------------------------------
+namespace sigma {
+int row_norm_launch(const RowNormParams &p, cudaStream_t stream);
+int dwconv3x3_silu_launch(const float *x, long long x_row_stride, long long x_batch_stride, const float *w,
+                          const float *bias, float *y, long long y_batch_stride, int batch, int H, int W, int D,
+                          cudaStream_t stream);
+size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N);
+int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
+                  const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
+                  size_t ws_bytes, int force_split, cudaStream_t stream);
+static bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+}  // namespace sigma
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int sigma_layernorm_fwd(const float *x, const float *w, const float *b, float *y, int64_t rows, int C, float eps,
+                        void *stream) {
+  SIGMA_CHECK_ARG(x && w && b && y, "sigma_layernorm_fwd: null pointer");
+  SIGMA_CHECK_ARG(C > 0 && C % 4 == 0 && rows >= 0, "sigma_layernorm_fwd: C=%d must be a positive multiple of 4", C);
+  SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(y), "sigma_layernorm_fwd: pointers must be 16-byte aligned");
+  RowNormParams p{x, 0, 1, w, b, nullptr, 0, nullptr, y, rows, rows > 0 ? rows : 1, 0, 0, C, C, eps};
+  return row_norm_launch(p, (cudaStream_t)stream);
+}
+
+int sigma_merge_norm_gate_fwd(const float *y, int K, int64_t k_stride, int64_t in_batch_stride, const float *gamma,
+                              const float *beta, const float *z, int64_t z_row_stride, const float *gate, float *out,
+                              int64_t out_batch_stride, int64_t out_row_stride, int64_t rows, int64_t rows_per_batch,
+                              int D, float eps, void *stream) {
+  SIGMA_CHECK_ARG(y && gamma && beta && out, "sigma_merge_norm_gate_fwd: null pointer");
+  SIGMA_CHECK_ARG(K >= 1 && K <= 8 && D > 0 && D % 4 == 0 && rows >= 0 && rows_per_batch > 0,
+                  "sigma_merge_norm_gate_fwd: bad sizes K=%d D=%d rows=%lld rows_per_batch=%lld", K, D, (long long)rows,
+                  (long long)rows_per_batch);
+  SIGMA_CHECK_ARG(al16(y) && al16(gamma) && al16(beta) && al16(out) && al16(z) && al16(gate) && k_stride % 4 == 0 &&
+                      in_batch_stride % 4 == 0 && out_batch_stride % 4 == 0 && out_row_stride % 4 == 0 &&
+                      z_row_stride % 4 == 0,
+                  "sigma_merge_norm_gate_fwd: pointers / strides must be 16-byte aligned");
+  RowNormParams p{y, k_stride, K, gamma, beta, z, z_row_stride, gate, out, rows, rows_per_batch, in_batch_stride,
+                  out_batch_stride, out_row_stride, D, eps};
+  return row_norm_launch(p, (cudaStream_t)stream);
+}
+
+int sigma_dwconv3x3_silu_fwd(const float *x, int64_t x_row_stride, int64_t x_batch_stride, const float *w,
+                             const float *bias, float *y, int64_t y_batch_stride, int batch, int H, int W, int D,
+                             void *stream) {
+  SIGMA_CHECK_ARG(x && w && y, "sigma_dwconv3x3_silu_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && D > 0 && D % 4 == 0, "sigma_dwconv3x3_silu_fwd: bad sizes");
+  SIGMA_CHECK_ARG(al16(x) && al16(y) && x_row_stride % 4 == 0 && x_batch_stride % 4 == 0 && y_batch_stride % 4 == 0,
+                  "sigma_dwconv3x3_silu_fwd: pointers / strides must be 16-byte aligned");
+  return dwconv3x3_silu_launch(x, x_row_stride, x_batch_stride, w, bias, y, y_batch_stride, batch, H, W, D,
+                               (cudaStream_t)stream);
+}
+
+int sigma_ss2d_padded_cp(int N, int R) {
+  const int opts[] = {4, 8, 12, 16, 24, 32, 48, 64};
+  for (int o : opts)
+    if (R <= o) return 2 * N + o;
+  return -1;
+}
+
+size_t sigma_ss2d_scan_workspace_bytes(int kind, int batch, int H, int W, int D, int N) {
+  (void)H; (void)W;
+  return ss2d_scan_workspace_bytes(kind, batch, D, N);
+}
+
+static int ss2d_check(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
+                      const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp) {
+  SIGMA_CHECK_ARG(xc && xdbl && dtw && dtb && A && Ds && y, "sigma_ss2d_scan_fwd: null pointer");
+  SIGMA_CHECK_ARG(kind == SIGMA_DIRS_CROSS4 || kind == SIGMA_DIRS_SEQ2 || kind == SIGMA_DIRS_CROSS,
+                  "sigma_ss2d_scan_fwd: unknown kind %d", kind);
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && D > 0 && D % 4 == 0 && R > 0, "sigma_ss2d_scan_fwd: bad sizes");
+  SIGMA_CHECK_ARG(kind != SIGMA_DIRS_CROSS || batch % 2 == 0, "sigma_ss2d_scan_fwd: CROSS needs batch = 2·images");
+  SIGMA_CHECK_ARG(N == 4 || N == 8 || N == 16, "sigma_ss2d_scan_fwd: d_state=%d unsupported (4, 8, 16)", N);
+  SIGMA_CHECK_ARG(Cp == sigma_ss2d_padded_cp(N, R), "sigma_ss2d_scan_fwd: Cp=%d must equal sigma_ss2d_padded_cp(N=%d, R=%d)=%d",
+                  Cp, N, R, sigma_ss2d_padded_cp(N, R));
+  SIGMA_CHECK_ARG(al16(xc) && al16(xdbl) && al16(y), "sigma_ss2d_scan_fwd: xc / xdbl / y must be 16-byte aligned");
+  return SIGMA_OK;
+}
+
+int sigma_ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb,
+                        const float *A, const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = ss2d_check(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp);
+  if (rc) return rc;
+  return ss2d_scan_fwd(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp, workspace, workspace_bytes, 0,
+                       (cudaStream_t)stream);
+}
+
+// test hook: force the number of L-segments
+int sigma_ss2d_scan_fwd_split(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb,
+                              const float *A, const float *Ds, float *y, int batch, int H, int W, int D, int N, int R,
+                              int Cp, void *workspace, size_t workspace_bytes, int nsplit, void *stream) {
+  int rc = ss2d_check(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp);
+  if (rc) return rc;
+  return ss2d_scan_fwd(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp, workspace, workspace_bytes, nsplit,
+                       (cudaStream_t)stream);
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

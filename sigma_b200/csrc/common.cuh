@@ -38,6 +38,21 @@ void count_launch(int n = 1);
     SIGMA_CHECK_CUDA(cudaPeekAtLastError());      \
   } while (0)
 
+// ---- shared host-side parameter blocks ----
+struct RowNormParams {
+  const float *y;          // K slabs
+  long long k_stride;      // floats between slabs
+  int K;
+  const float *gamma, *beta;
+  const float *z; long long z_row_stride;       // nullable
+  const float *gate;                            // nullable, (rows / rows_per_batch, D)
+  float *out;
+  long long rows, rows_per_batch;
+  long long in_batch_stride, out_batch_stride, out_row_stride;
+  int D;
+  float eps;
+};
+
 // ---- device math ----
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -45,14 +60,26 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// F.softplus with the default threshold 20 (selective_scan_fwd_kernel.cuh:133,
-// selective_scan_interface.py:107).  log1pf keeps small deltas accurate (delta ~ 1e-3 is the
-// common case after dt_init); the exp argument is <= 20 so the fast exp is safe.
-__device__ __forceinline__ float softplus20(float x) {
-  return x <= 20.f ? log1pf(ex2(x * kLog2e)) : x;
+__device__ __forceinline__ float lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-__device__ __forceinline__ float silu(float x) { return x / (1.f + ex2(-x * kLog2e)); }
+// F.softplus with the default threshold 20 (selective_scan_fwd_kernel.cuh:133,
+// selective_scan_interface.py:107), branch-free so it schedules inside the scan's inner loop:
+//   softplus(x) = max(x,0) + log1p(z),  z = exp(-|x|) in (0,1]
+// log1p(z): 4-term series for z < 2^-6 (rel. err < 1e-8; keeps delta ~ 1e-3..1e-5 accurate, the common
+// case after dt_init), MUFU.LG2 of 1+z otherwise (rel. err < 1e-5 there).  For x > 20, z < 2.1e-9 and the
+// sum rounds to x, which is exactly the reference's thresholded branch.
+__device__ __forceinline__ float softplus20(float x) {
+  const float z = ex2(-fabsf(x) * kLog2e);
+  const float poly = z * fmaf(z, fmaf(z, fmaf(z, -0.25f, 0.33333334f), -0.5f), 1.0f);
+  const float lg = lg2(1.0f + z) * 0.6931471805599453f;
+  return fmaxf(x, 0.f) + (z < 0.015625f ? poly : lg);
+}
+
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + ex2(-x * kLog2e)); }
 
 // ---- cp.async (LDGSTS) ----
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {

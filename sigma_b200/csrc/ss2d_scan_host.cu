@@ -1,0 +1,148 @@
+// Host side of the fused SS2D scan: tensor maps, L-segment planning, dispatch (sigma_ss2d_scan_fwd).
+#include <algorithm>
+
+#include "ss2d_scan.cuh"
+
+namespace sigma {
+
+// ---- tensor map creation through the runtime-resolved driver entry point ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || ptr == nullptr) {
+    set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed: %s", cudaGetErrorString(e));
+    return nullptr;
+  }
+  fn = (EncodeTiledFn)ptr;
+  return fn;
+}
+
+int make_tmap_f32_4d(CUtensorMap *map, const void *base, const uint64_t dims[4], const uint64_t strides_bytes[3],
+                     const uint32_t box[4]) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return SIGMA_ECUDA;
+  cuuint64_t gdim[4] = {dims[0], dims[1], dims[2], dims[3]};
+  cuuint64_t gstr[3] = {strides_bytes[0], strides_bytes[1], strides_bytes[2]};
+  cuuint32_t bdim[4] = {box[0], box[1], box[2], box[3]};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (CUresult %d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) "
+              "box=(%u,%u,%u,%u) base=%p",
+              (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+              (unsigned long long)dims[3], (unsigned long long)strides_bytes[0], (unsigned long long)strides_bytes[1],
+              (unsigned long long)strides_bytes[2], box[0], box[1], box[2], box[3], base);
+    return SIGMA_ECUDA;
+  }
+  return SIGMA_OK;
+}
+
+static int pad_rp(int R) {
+  const int opts[] = {4, 8, 12, 16, 24, 32, 48, 64};
+  for (int o : opts)
+    if (R <= o) return o;
+  return -1;
+}
+
+template <int SPT, int LPC>
+static int dispatch_rp(const Ss2dParams &p, int ndir, cudaStream_t s) {
+  switch (pad_rp(p.R)) {
+    case 4: return ss2d_launch<SPT, LPC, 4>(p, ndir, s);
+    case 8: return ss2d_launch<SPT, LPC, 8>(p, ndir, s);
+    case 12: return ss2d_launch<SPT, LPC, 12>(p, ndir, s);
+    case 16: return ss2d_launch<SPT, LPC, 16>(p, ndir, s);
+    case 24: return ss2d_launch<SPT, LPC, 24>(p, ndir, s);
+    case 32: return ss2d_launch<SPT, LPC, 32>(p, ndir, s);
+    case 48: return ss2d_launch<SPT, LPC, 48>(p, ndir, s);
+    case 64: return ss2d_launch<SPT, LPC, 64>(p, ndir, s);
+  }
+  set_error("sigma_ss2d_scan_fwd: dt_rank %d > 64 unsupported", p.R);
+  return SIGMA_EUNSUPPORTED;
+}
+
+static int kind_dirs(int kind) { return kind == SIGMA_DIRS_CROSS4 ? 4 : (kind == SIGMA_DIRS_SEQ2 ? 2 : 1); }
+static int lt_for(int N) { return N >= 8 ? Ss2dCfg<4>::LT : Ss2dCfg<1>::LT; }
+static int dt_for(int N) { return N == 16 ? Ss2dCfg<4>::DT : (N == 8 ? Ss2dCfg<2>::DT : Ss2dCfg<1>::DT); }
+static int nw_for(int N) { return N == 16 ? Ss2dCfg<4>::NW : (N == 8 ? Ss2dCfg<2>::NW : Ss2dCfg<1>::NW); }
+
+constexpr int kMaxSplit = 32;
+
+size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N) {
+  return (size_t)batch * kind_dirs(kind) * D * kMaxSplit * 2 * N * sizeof(float);
+}
+
+int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
+                  const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
+                  size_t ws_bytes, int force_split, cudaStream_t stream) {
+  Ss2dParams p;
+  memset(&p, 0, sizeof(p));
+  p.dtw = dtw; p.dtb = dtb; p.A = A; p.Ds = Ds; p.carry = (float *)ws;
+  p.D = D; p.N = N; p.R = R; p.Cp = Cp; p.kind = kind; p.batch = batch;
+  const int ndir = kind_dirs(kind);
+  const int K = kind == SIGMA_DIRS_CROSS ? 1 : ndir;        // x_dbl rows per position
+  const long long Lseq = kind == SIGMA_DIRS_SEQ2 ? 2LL * H * W : (long long)H * W;
+  const int LT = lt_for(N), DT = dt_for(N);
+  int rc;
+  int max_tiles = 0;
+  for (int k = 0; k < ndir; ++k) {
+    const bool colmajor = kind == SIGMA_DIRS_CROSS4 && (k & 1);
+    p.rev[k] = (kind == SIGMA_DIRS_CROSS4) ? (k >= 2) : (kind == SIGMA_DIRS_SEQ2 ? (k == 1) : 0);
+    uint64_t dims[4], str[3];
+    uint32_t box[4] = {(uint32_t)DT, (uint32_t)LT, 1, 1};
+    // channels-last activations (batch, Lseq, D)
+    if (!colmajor) {
+      p.I[k] = (int)Lseq; p.O[k] = 1;
+      dims[0] = D; dims[1] = Lseq; dims[2] = 1; dims[3] = batch;
+      str[0] = (uint64_t)D * 4; str[1] = (uint64_t)Lseq * D * 4; str[2] = (uint64_t)Lseq * D * 4;
+    } else {  // walk h (inner) at fixed w (outer): l1 = w·H + h  <->  position h·W + w   (vmamba.py:87)
+      p.I[k] = H; p.O[k] = W;
+      dims[0] = D; dims[1] = H; dims[2] = W; dims[3] = batch;
+      str[0] = (uint64_t)W * D * 4; str[1] = (uint64_t)D * 4; str[2] = (uint64_t)Lseq * D * 4;
+    }
+    if ((rc = make_tmap_f32_4d(&p.m_xc[k], xc, dims, str, box))) return rc;
+    if ((rc = make_tmap_f32_4d(&p.m_y[k], y + (long long)k * batch * Lseq * D, dims, str, box))) return rc;
+    // x_dbl (batch, Lseq, K, Cp): direction k's row starts at column k·Cp
+    uint32_t boxd[4] = {(uint32_t)Cp, (uint32_t)LT, 1, 1};
+    dims[0] = Cp;
+    const uint64_t pos = (uint64_t)K * Cp * 4;
+    if (!colmajor) { str[0] = pos; str[1] = Lseq * pos; str[2] = Lseq * pos; }
+    else { str[0] = W * pos; str[1] = pos; str[2] = Lseq * pos; }
+    if ((rc = make_tmap_f32_4d(&p.m_dbl[k], xdbl + (long long)(kind == SIGMA_DIRS_CROSS ? 0 : k) * Cp, dims, str, boxd)))
+      return rc;
+    max_tiles = std::max(max_tiles, p.O[k] * ((p.I[k] + LT - 1) / LT));
+  }
+  // L-segments: only when the unsplit grid cannot fill the machine (each split doubles the exp work)
+  const long long ctas = (long long)((D + DT - 1) / DT) * ndir * batch;
+  const long long warps = ctas * nw_for(N);
+  int nsplit = 1;
+  const long long target = 148LL * 16;
+  if (warps * 2 <= target) nsplit = (int)std::min<long long>((target + warps - 1) / warps, kMaxSplit);
+  if (force_split > 0) nsplit = std::min(force_split, kMaxSplit);
+  if (ws == nullptr || ws_bytes < ss2d_scan_workspace_bytes(kind, batch, D, N)) {
+    if (force_split > 1) { set_error("sigma_ss2d_scan_fwd: workspace too small for %d segments", force_split); return SIGMA_EWORKSPACE; }
+    nsplit = 1;
+  }
+  nsplit = std::max(1, std::min(nsplit, max_tiles));
+  // all directions share tiles_per_split; directions with fewer tiles simply get empty trailing segments
+  p.tiles_per_split = (max_tiles + nsplit - 1) / nsplit;
+  p.nsplit = nsplit;
+
+  switch (N) {
+    case 4: return dispatch_rp<4, 1>(p, ndir, stream);
+    case 8: return dispatch_rp<4, 2>(p, ndir, stream);
+    case 16: return dispatch_rp<4, 4>(p, ndir, stream);
+  }
+  set_error("sigma_ss2d_scan_fwd: d_state=%d unsupported by the fused kernel (4, 8, 16)", N);
+  return SIGMA_EUNSUPPORTED;
+}
+
+}  // namespace sigma

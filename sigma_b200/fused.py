@@ -1,0 +1,234 @@
+"""Inference pipeline of the Sigma hot path over libsigma_b200 (channels-last, fp32 storage).
+
+Per SS2D block (vmamba.py:1067-1089 + cross_selective_scan :165-226) the kernels are
+    LayerNorm -> in_proj GEMM -> dwconv3x3+SiLU -> x_proj GEMM (all 4 directions in one) ->
+    fused 4-direction scan (CrossScan index math + dt_proj + softplus + scan, TMA-staged) ->
+    merge(4) + out_norm + ·SiLU(z) -> out_proj GEMM (+ residual)
+so neither CrossScan's (B,4,D,L) copy, nor delta (B,4D,L), nor CrossMerge's transposes ever exist.
+Dense projections go through `linear()` (see there).  Everything here assumes no autograd.
+"""
+import ctypes
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+EPS = 1e-5
+_FORCE_SPLIT = 0  # test hook: force the number of L-segments of the fused scan
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ---------------------------------------------------------------- primitive wrappers
+def layernorm(x2d, ln):
+    """nn.LayerNorm over the last dim of a contiguous (rows, C) tensor."""
+    rows, C = x2d.shape
+    y = torch.empty_like(x2d)
+    _lib.check(_lib.lib().sigma_layernorm_fwd(_p(x2d), _p(ln.weight), _p(ln.bias), _p(y), rows, C, float(ln.eps), _stream()),
+               "sigma_layernorm_fwd")
+    return y
+
+
+def linear(x2d, weight, bias=None, out=None):
+    """Dense projection y = x·W^T (+b).  Plain library GEMM (cuBLAS through torch) in this round; the
+    tcgen05/TMEM replacement slots in here."""
+    if out is None:
+        return F.linear(x2d, weight, bias)
+    torch.mm(x2d, weight.t(), out=out)
+    if bias is not None:
+        out += bias
+    return out
+
+
+def dwconv3x3_silu(x, x_row_stride, x_batch_stride, conv, out, out_batch_stride, batch, H, W, D):
+    _lib.check(_lib.lib().sigma_dwconv3x3_silu_fwd(_p(x), x_row_stride, x_batch_stride, _p(conv.weight), _p(conv.bias),
+                                                   _p(out), out_batch_stride, batch, H, W, D, _stream()),
+               "sigma_dwconv3x3_silu_fwd")
+    return out
+
+
+def ss2d_scan(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
+    L_ = _lib.lib()
+    ndir = {_lib.DIRS_CROSS4: 4, _lib.DIRS_SEQ2: 2, _lib.DIRS_CROSS: 1}[kind]
+    Lseq = 2 * H * W if kind == _lib.DIRS_SEQ2 else H * W
+    y = torch.empty((ndir, batch, Lseq, D), dtype=torch.float32, device=xc.device)
+    wsb = L_.sigma_ss2d_scan_workspace_bytes(kind, batch, H, W, D, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=xc.device)
+    if _FORCE_SPLIT:
+        rc = L_.sigma_ss2d_scan_fwd_split(kind, _p(xc), _p(xdbl), _p(dtw), _p(dtb), _p(A), _p(Ds), _p(y), batch, H, W, D, N,
+                                          R, Cp, _p(ws), wsb, _FORCE_SPLIT, _stream())
+    else:
+        rc = L_.sigma_ss2d_scan_fwd(kind, _p(xc), _p(xdbl), _p(dtw), _p(dtb), _p(A), _p(Ds), _p(y), batch, H, W, D, N, R, Cp,
+                                    _p(ws), wsb, _stream())
+    _lib.check(rc, "sigma_ss2d_scan_fwd")
+    return y
+
+
+def merge_norm_gate(y, K, k_stride, in_batch_stride, ln, z, z_row_stride, gate, out, out_batch_stride, out_row_stride,
+                    rows, rows_per_batch, D, y_offset=0, out_offset=0):
+    yp = ctypes.c_void_p(y.data_ptr() + 4 * y_offset)
+    op = ctypes.c_void_p(out.data_ptr() + 4 * out_offset)
+    rc = _lib.lib().sigma_merge_norm_gate_fwd(yp, K, k_stride, in_batch_stride, _p(ln.weight), _p(ln.bias), z, z_row_stride,
+                                              _p(gate), op, out_batch_stride, out_row_stride, rows, rows_per_batch, D,
+                                              float(ln.eps), _stream())
+    _lib.check(rc, "sigma_merge_norm_gate_fwd")
+    return out
+
+
+# ---------------------------------------------------------------- per-module packed parameters
+def _pack_xproj(w, N, R, Cp):
+    """x_proj rows [dt (R) | B (N) | C (N)] (vmamba.py:198) -> kernel row order [B | C | dt | 0-pad]."""
+    pad = w.new_zeros((Cp - 2 * N - R, w.shape[1]))
+    return torch.cat([w[R:R + N], w[R + N:R + 2 * N], w[:R], pad], dim=0)
+
+
+def _cache(m, key, versions, build):
+    c = m.__dict__.setdefault("_sigma_cache", {})
+    ent = c.get(key)
+    if ent is None or ent[0] != versions:
+        ent = (versions, build())
+        c[key] = ent
+    return ent[1]
+
+
+def _ssm_params(m):
+    """Packed, contiguous fp32 SSM parameters of SS2D / ConMB_SS2D (K directions)."""
+    ps = (m.x_proj_weight, m.dt_projs_weight, m.dt_projs_bias, m.A_logs, m.Ds)
+    ver = tuple((p._version, p.data_ptr()) for p in ps)
+
+    def build():
+        N, R = m.d_state, m.dt_rank
+        Cp = _lib.lib().sigma_ss2d_padded_cp(N, R)
+        if Cp < 0:
+            raise RuntimeError(f"dt_rank={R} > 64 is not supported by the fused scan")
+        xw = torch.cat([_pack_xproj(m.x_proj_weight[k].float(), N, R, Cp) for k in range(m.K)], dim=0).contiguous()
+        return dict(Cp=Cp, xproj=xw, dtw=m.dt_projs_weight.float().contiguous(), dtb=m.dt_projs_bias.float().contiguous(),
+                    A=(-torch.exp(m.A_logs.float())).contiguous(), Ds=m.Ds.float().contiguous())
+    return _cache(m, "ssm", ver, build)
+
+
+def _cma_params(cm):
+    """Cross_Mamba_Attention_SSM: modality 0 = rgb (x_proj_1, ...), modality 1 = x."""
+    ps = (cm.x_proj_1.weight, cm.x_proj_2.weight, cm.dt_proj_1.weight, cm.dt_proj_2.weight, cm.dt_proj_1.bias,
+          cm.dt_proj_2.bias, cm.A_log_1, cm.A_log_2, cm.D_1, cm.D_2)
+    ver = tuple((p._version, p.data_ptr()) for p in ps)
+
+    def build():
+        N, R = cm.d_state, cm.dt_rank
+        Cp = _lib.lib().sigma_ss2d_padded_cp(N, R)
+        return dict(Cp=Cp, xproj1=_pack_xproj(cm.x_proj_1.weight.float(), N, R, Cp).contiguous(),
+                    xproj2=_pack_xproj(cm.x_proj_2.weight.float(), N, R, Cp).contiguous(),
+                    dtw=torch.stack([cm.dt_proj_1.weight, cm.dt_proj_2.weight]).float().contiguous(),
+                    dtb=torch.stack([cm.dt_proj_1.bias, cm.dt_proj_2.bias]).float().contiguous(),
+                    A=(-torch.exp(torch.cat([cm.A_log_1, cm.A_log_2]).float())).contiguous(),
+                    Ds=torch.cat([cm.D_1, cm.D_2]).float().contiguous())
+    return _cache(cm, "cma", ver, build)
+
+
+# ---------------------------------------------------------------- blocks
+def ss2d(m, x, residual=None):
+    """SS2D.forward (vmamba.py:1067-1089); x (B,H,W,C) contiguous.  Returns (B,H,W,C) [+ residual]."""
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    D, N, R, L = m.d_inner, m.d_state, m.dt_rank, H * W
+    c = _ssm_params(m)
+    xz = linear(x.view(B * L, C), m.in_proj.weight, m.in_proj.bias)                                    # (BL, 2D): [x | z]
+    xc = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
+    dwconv3x3_silu(xz, 2 * D, L * 2 * D, m.conv2d, xc, L * D, B, H, W, D)
+    xdbl = linear(xc.view(B * L, D), c["xproj"])                                                       # (BL, 4·Cp)
+    y = ss2d_scan(_lib.DIRS_CROSS4, xc, xdbl, c["dtw"], c["dtb"], c["A"], c["Ds"], B, H, W, D, N, R, c["Cp"])
+    yg = torch.empty((B * L, D), dtype=torch.float32, device=x.device)
+    z = ctypes.c_void_p(xz.data_ptr() + 4 * D)
+    merge_norm_gate(y, 4, B * L * D, 0, m.out_norm, z, 2 * D, None, yg, 0, D, B * L, B * L, D)
+    out = linear(yg, m.out_proj.weight, m.out_proj.bias).view(B, H, W, C)
+    return out if residual is None else residual + out
+
+
+def vss_block(blk, x):
+    """VSSBlock._forward (vmamba.py:1712-1716), mlp_ratio = 0."""
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    xn = layernorm(x.view(-1, C), blk.norm).view(B, H, W, C)
+    return ss2d(blk.op, xn, residual=x)
+
+
+def patch_merging(m, x):
+    """PatchMerging2D (vmamba.py:619-636)."""
+    H, W = x.shape[1:3]
+    if (W % 2) or (H % 2):
+        x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+    x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
+    B, H2, W2, C4 = x.shape
+    xn = layernorm(x.view(-1, C4), m.norm)
+    return linear(xn, m.reduction.weight).view(B, H2, W2, -1)
+
+
+def cromb_ss2d(m, x_rgb, x_e, residual=False):
+    """CrossMambaFusion_SS2D_SSM.forward (vmamba.py:1622-1640) + Cross_Mamba_Attention_SSM.forward (:1508-1545)."""
+    x_rgb, x_e = x_rgb.contiguous(), x_e.contiguous()
+    B, H, W, C = x_rgb.shape
+    D, L = m.d_inner, H * W
+    cm = m.CMA_ssm
+    N, R = cm.d_state, cm.dt_rank
+    c = _cma_params(cm)
+    dev = x_rgb.device
+    xp = torch.empty((2, B * L, D), dtype=torch.float32, device=dev)          # modality-major
+    linear(x_rgb.view(B * L, C), m.in_proj.weight, m.in_proj.bias, out=xp[0])
+    linear(x_e.view(B * L, C), m.in_proj_modalx.weight, m.in_proj_modalx.bias, out=xp[1])
+    xc = torch.empty((2 * B, L, D), dtype=torch.float32, device=dev)
+    dwconv3x3_silu(xp, D, L * D, m.conv2d, xc, L * D, 2 * B, H, W, D)         # ONE conv for both modalities (:1629-1630)
+    xdbl = torch.empty((2, B * L, c["Cp"]), dtype=torch.float32, device=dev)
+    linear(xc[:B].view(B * L, D), c["xproj1"], out=xdbl[0])
+    linear(xc[B:].view(B * L, D), c["xproj2"], out=xdbl[1])
+    y = ss2d_scan(_lib.DIRS_CROSS, xc, xdbl, c["dtw"], c["dtb"], c["A"], c["Ds"], 2 * B, H, W, D, N, R, c["Cp"])  # (1,2B,L,D)
+    yn = torch.empty((2, B * L, D), dtype=torch.float32, device=dev)
+    merge_norm_gate(y, 1, 0, 0, cm.out_norm_1, None, 0, None, yn, 0, D, B * L, B * L, D)
+    merge_norm_gate(y, 1, 0, 0, cm.out_norm_2, None, 0, None, yn, 0, D, B * L, B * L, D, y_offset=B * L * D, out_offset=B * L * D)
+    o_r = linear(yn[0], m.out_proj_rgb.weight, m.out_proj_rgb.bias).view(B, H, W, C)
+    o_e = linear(yn[1], m.out_proj_e.weight, m.out_proj_e.bias).view(B, H, W, C)
+    return (x_rgb + o_r, x_e + o_e) if residual else (o_r, o_e)
+
+
+def conmb_ss2d(m, x_rgb, x_e, residual=None):
+    """ConMB_SS2D.forward (vmamba.py:1265-1284) + cross_selective_scan_multimodal_k2 (:369-430)."""
+    x_rgb, x_e = x_rgb.contiguous(), x_e.contiguous()
+    B, H, W, C = x_rgb.shape
+    D, N, R, L = m.d_inner, m.d_state, m.dt_rank, H * W
+    c = _ssm_params(m)
+    dev = x_rgb.device
+    tr = linear(x_rgb.view(B * L, C), m.in_proj.weight, m.in_proj.bias)
+    te = linear(x_e.view(B * L, C), m.in_proj_modalx.weight, m.in_proj_modalx.bias)
+    seq = torch.empty((B, 2 * L, D), dtype=torch.float32, device=dev)         # [rgb ‖ x] along L (vmamba.py:130)
+    dwconv3x3_silu(tr, D, L * D, m.conv2d, seq, 2 * L * D, B, H, W, D)
+    dwconv3x3_silu(te, D, L * D, m.conv2d_modalx, seq[:, L:], 2 * L * D, B, H, W, D)
+    xdbl = linear(seq.view(B * 2 * L, D), c["xproj"])                         # (B·2L, 2·Cp)
+    y = ss2d_scan(_lib.DIRS_SEQ2, seq, xdbl, c["dtw"], c["dtb"], c["A"], c["Ds"], B, H, W, D, N, R, c["Cp"])  # (2,B,2L,D)
+    # SE gates from the PRE-conv projections, applied crosswise (vmamba.py:1276-1281)
+    g_r = m.fc1(tr.view(B, L, D).mean(dim=1))
+    g_e = m.fc2(te.view(B, L, D).mean(dim=1))
+    ycat = torch.empty((B * L, 2 * D), dtype=torch.float32, device=dev)
+    ks = B * 2 * L * D
+    merge_norm_gate(y, 2, ks, 2 * L * D, m.out_norm1, None, 0, g_e, ycat, L * 2 * D, 2 * D, B * L, L, D)
+    merge_norm_gate(y, 2, ks, 2 * L * D, m.out_norm2, None, 0, g_r, ycat, L * 2 * D, 2 * D, B * L, L, D,
+                    y_offset=L * D, out_offset=D)
+    out = linear(ycat, m.out_proj.weight, m.out_proj.bias).view(B, H, W, C)
+    return out if residual is None else residual + out
+
+
+def cvss_decoder_block(blk, x):
+    """CVSSDecoderBlock._forward (vmamba.py:1800-1805)."""
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    xn = layernorm(x.view(-1, C), blk.norm1).view(B, H, W, C)
+    x1 = ss2d(blk.op, xn, residual=x * blk.scale1)
+    xn2 = layernorm(x1.view(-1, C), blk.norm2).view(B, H, W, C)
+    t = blk.conv_blk(xn2.permute(0, 3, 1, 2))            # channels_last view: cuDNN NHWC convs, no copy
+    y = t + (x1 * blk.scale2).permute(0, 3, 1, 2)
+    return y.permute(0, 2, 3, 1).contiguous()

@@ -1,0 +1,143 @@
+"""GPU: the fused channels-last multi-direction scan (sigma_ss2d_scan_fwd) and the row-wise kernels
+through the C-ABI, against the CPU oracle built from the reference's own definitions:
+direction maps vmamba.py:80-121 / 123-163, dt_proj vmamba.py:199, selective_scan_ref."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import procedural as P
+from helpers import assert_close
+from oracle import scan_oracle
+
+pytestmark = pytest.mark.gpu
+S = 21
+
+
+def _dir_index(kind, H, W):
+    """position visited at scan step l, per direction (SURVEY.md App. A 'Direction maps')."""
+    L = H * W
+    if kind == "cross4":
+        row = np.arange(L)
+        col = (np.arange(H)[None, :] * W + np.arange(W)[:, None]).reshape(-1)      # l1 = w·H + h -> h·W + w
+        return [row, col, row[::-1].copy(), col[::-1].copy()]
+    if kind == "seq2":
+        a = np.arange(2 * L)
+        return [a, a[::-1].copy()]
+    return [np.arange(L)]
+
+
+def _reference(kind, xc, xdbl, dtw, dtb, A, Ds, H, W, N, R):
+    xc, xdbl, dtw, dtb, A, Ds = (t.numpy() for t in (xc, xdbl, dtw, dtb, A, Ds))
+    Bt, Ls, D = xc.shape
+    idx = _dir_index(kind, H, W)
+    K = len(idx)
+    y = np.zeros((K, Bt, Ls, D), np.float32)
+    if kind == "cross":
+        half = Bt // 2
+        for m in range(2):
+            sl = slice(m * half, (m + 1) * half)
+            osl = slice((1 - m) * half, (2 - m) * half)
+            u = xc[sl].transpose(0, 2, 1)                                             # (b, D, L)
+            dt = np.einsum("blr,dr->bdl", xdbl[sl, :, 0, 2 * N:2 * N + R], dtw[m])
+            Bm = xdbl[sl, :, 0, 0:N].transpose(0, 2, 1)[:, None]
+            Cm = xdbl[osl, :, 0, N:2 * N].transpose(0, 2, 1)[:, None]                   # C of the other modality
+            o = scan_oracle.scan_fwd(u, dt, A[m * D:(m + 1) * D], Bm, Cm, Ds[m * D:(m + 1) * D], dtb[m], True)
+            y[0, sl] = o.transpose(0, 2, 1)
+        return y
+    us, dts, Bs, Cs = [], [], [], []
+    for k, ix in enumerate(idx):
+        us.append(xc[:, ix].transpose(0, 2, 1))
+        dts.append(np.einsum("blr,dr->bdl", xdbl[:, ix, k, 2 * N:2 * N + R], dtw[k]))
+        Bs.append(xdbl[:, ix, k, 0:N].transpose(0, 2, 1))
+        Cs.append(xdbl[:, ix, k, N:2 * N].transpose(0, 2, 1))
+    u = np.concatenate(us, 1)
+    dt = np.concatenate(dts, 1)
+    o = scan_oracle.scan_fwd(u, dt, A, np.stack(Bs, 1), np.stack(Cs, 1), Ds, dtb.reshape(-1), True)
+    for k, ix in enumerate(idx):
+        y[k][:, ix] = o[:, k * D:(k + 1) * D].transpose(0, 2, 1)
+    return y
+
+
+CASES = [  # kind, B(images), H, W, D, N, R
+    ("cross4", 2, 6, 5, 64, 16, 2), ("cross4", 1, 15, 20, 192, 16, 6), ("cross4", 2, 40, 33, 96, 4, 6),
+    ("cross4", 1, 30, 40, 80, 16, 12), ("cross4", 1, 7, 9, 768, 4, 24), ("cross4", 1, 9, 13, 128, 8, 5),
+    ("seq2", 2, 6, 5, 64, 4, 2), ("seq2", 1, 30, 41, 384, 4, 12), ("cross", 2, 6, 5, 64, 4, 2), ("cross", 1, 31, 40, 192, 4, 6),
+    ("cross4", 1, 10, 12, 64, 16, 48), ("cross4", 1, 10, 12, 64, 4, 64),
+]
+
+
+@pytest.mark.parametrize("kind,B,H,W,D,N,R", CASES)
+@pytest.mark.parametrize("split", [0, 1, 3])
+def test_fused_scan_matches_oracle(kind, B, H, W, D, N, R, split):
+    from sigma_b200 import _lib, fused
+    L = H * W
+    Kx = {"cross4": 4, "seq2": 2, "cross": 1}[kind]
+    Kw = 2 if kind == "cross" else Kx
+    Bt = 2 * B if kind == "cross" else B
+    Ls = 2 * L if kind == "seq2" else L
+    Cp = _lib.lib().sigma_ss2d_padded_cp(N, R)
+    tag = f"{kind}/{B}/{H}/{W}/{D}/{N}/{R}"
+    xc = P.randn(S, tag + "/xc", (Bt, Ls, D))
+    xdbl = P.randn(S, tag + "/xdbl", (Bt, Ls, Kx, Cp))
+    xdbl[..., 2 * N + R:] = 0.0                                   # zero padding columns, as the packed x_proj produces
+    dtw = P.rand(S, tag + "/dtw", (Kw, D, R), -R ** -0.5, R ** -0.5)
+    dtb = P.rand(S, tag + "/dtb", (Kw, D), -6.0, -1.0)
+    A = -P.rand(S, tag + "/A", (Kw * D, N), 0.3, N + 0.5)
+    Ds = P.randn(S, tag + "/Ds", (Kw * D,))
+    ref = _reference(kind, xc, xdbl, dtw, dtb, A, Ds, H, W, N, R)
+    kid = {"cross4": _lib.DIRS_CROSS4, "seq2": _lib.DIRS_SEQ2, "cross": _lib.DIRS_CROSS}[kind]
+    fused._FORCE_SPLIT = split
+    try:
+        y = fused.ss2d_scan(kid, xc.cuda(), xdbl.cuda(), dtw.cuda(), dtb.cuda(), A.cuda(), Ds.cuda(), Bt, H, W, D, N, R, Cp)
+        torch.cuda.synchronize()
+    finally:
+        fused._FORCE_SPLIT = 0
+    scale = float(np.abs(ref).max())
+    assert_close(y, ref, 6e-4, 1e-3 * scale, f"{tag} split={split}")
+
+
+@pytest.mark.parametrize("rows,C", [(7, 32), (100, 96), (33, 192), (5, 768), (9, 3072), (3, 4096)])
+def test_layernorm(rows, C):
+    from sigma_b200 import fused
+    x = P.randn(S, f"ln/{rows}/{C}", (rows, C), 2.0, 0.5)
+    ln = torch.nn.LayerNorm(C)
+    with torch.no_grad():
+        ln.weight.copy_(P.randn(S, "ln/w", (C,), 0.1, 1.0))
+        ln.bias.copy_(P.randn(S, "ln/b", (C,), 0.1))
+        ref = ln(x)
+        got = fused.layernorm(x.cuda(), ln.cuda())
+    assert_close(got, ref, 1e-5, 2e-5, f"layernorm {rows}x{C}")
+
+
+@pytest.mark.parametrize("B,H,W,D", [(2, 6, 5, 64), (1, 15, 20, 192), (3, 1, 7, 8), (1, 9, 1, 132)])
+def test_dwconv_silu(B, H, W, D):
+    from sigma_b200 import fused
+    conv = torch.nn.Conv2d(D, D, 3, padding=1, groups=D)
+    xz = P.randn(S, f"dw/{B}/{H}/{W}/{D}", (B, H, W, 2 * D))            # x is the first half of [x | z] rows
+    with torch.no_grad():
+        conv.weight.copy_(P.randn(S, "dw/w", (D, 1, 3, 3), 0.4))
+        conv.bias.copy_(P.randn(S, "dw/b", (D,), 0.2))
+        ref = torch.nn.functional.silu(conv(xz[..., :D].permute(0, 3, 1, 2))).permute(0, 2, 3, 1)
+        out = torch.empty((B, H * W, D), device="cuda")
+        fused.dwconv3x3_silu(xz.cuda(), 2 * D, H * W * 2 * D, conv.cuda(), out, H * W * D, B, H, W, D)
+    assert_close(out.view(B, H, W, D), ref, 1e-5, 1e-5, "dwconv+silu")
+
+
+def test_merge_norm_gate():
+    from sigma_b200 import fused
+    K, B, L, D = 4, 2, 37, 192
+    y = P.randn(S, "mng/y", (K, B * L, D))
+    z = P.randn(S, "mng/z", (B * L, 2 * D))
+    gate = P.rand(S, "mng/g", (B, D))
+    ln = torch.nn.LayerNorm(D)
+    with torch.no_grad():
+        ln.weight.copy_(P.randn(S, "mng/w", (D,), 0.1, 1.0))
+        ln.bias.copy_(P.randn(S, "mng/b", (D,), 0.1))
+        ref = ln(y.sum(0)) * torch.nn.functional.silu(z[:, D:]) * gate.repeat_interleave(L, 0)
+        out = torch.empty((B * L, D), device="cuda")
+        zc = z.cuda()
+        fused.merge_norm_gate(y.cuda(), K, B * L * D, L * D, ln.cuda(), ctypes.c_void_p(zc.data_ptr() + 4 * D), 2 * D,
+                              gate.cuda(), out, L * D, D, B * L, L, D)
+    assert_close(out, ref, 2e-5, 5e-5, "merge+norm+gate")
