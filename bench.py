@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""Headline benchmark: Sigma-tiny forward images/s on synthetic 480x640 RGB-X (BASELINE.json), plus the
+selective-scan kernel's achieved fraction of the HBM roofline and the reference's CPU path timed beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl sigma|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward of the whole network over one batch of B images per GPU (weak scaling: every
+rank runs its own B images, no data-path collective — the scan is per-sample).
+  value : images/s with the inputs already resident in HBM (CUDA-graph replay, CUDA events, max over ranks)
+  e2e   : the same through the public nn.Module call with HOST (pinned) inputs and logits read back to the
+          host inside the timed region
+  roofline / cpu_baseline : see DESIGN.md §Measurement.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+
+import torch  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--impl", default="sigma", choices=["sigma", "reference"])
+    ap.add_argument("--model", default="sigma_tiny")
+    ap.add_argument("--height", type=int, default=480)
+    ap.add_argument("--width", type=int, default=640)
+    ap.add_argument("--num-classes", type=int, default=9)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-images", type=int, default=3)
+    return ap.parse_args()
+
+
+def cfg_of(a):
+    import types
+    return types.SimpleNamespace(backbone=a.model, decoder="MambaDecoder", num_classes=a.num_classes,
+                                 image_height=a.height, image_width=a.width, pretrained_model=None, bn_eps=1e-3,
+                                 bn_momentum=0.1)
+
+
+def workload_name(a):
+    return f"{a.model} forward, synthetic RGB-X {a.height}x{a.width}, {a.num_classes} classes, random-init"
+
+
+# ------------------------------------------------------------------ CPU reference arm / cpu_baseline
+def cpu_reference_images_per_s(a, n_images, quiet=True):
+    """The oracle port of the reference's CPU path (oracle/sigma_ref.py + oracle/selective_scan_ref.c:
+    torch-CPU dense ops, multi-threaded C selective scan), one image at a time as engine/evaluator.py does."""
+    import contextlib
+    import io
+    from oracle import scan_oracle, sigma_ref
+    from sigma_b200 import modules as M
+    scan_oracle.build()
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.EncoderDecoder(cfg_of(a), criterion=None)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(1234)
+    rgb = torch.randn(1, 3, a.height, a.width, generator=g)
+    mx = torch.randn(1, 3, a.height, a.width, generator=g)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        for _ in range(n_images):
+            sigma_ref.encoder_decoder(rgb, mx, sd)
+        dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path (oracle port), rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(min(a.warmup, 1)):
+        cpu_reference_images_per_s(a, 1)
+    n = max(1, a.steps)
+    per_step = 1  # a step = a bounded sample of the batch: ONE image of the configured size
+    t0 = time.perf_counter()
+    ips, dt = cpu_reference_images_per_s(a, n * per_step)
+    line = {
+        "impl": "reference", "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(ips, 5), "unit": "images/s",
+        "n_gpus": a.gpus, "steps": n, "warmup": min(a.warmup, 1), "ms_per_step": round(1e3 * dt / n, 2),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": "1 image per step (bounded sample of the batch)"},
+        "cpu_baseline": {"value": round(ips, 5), "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{n} x 1 image {a.height}x{a.width}, oracle port (C selective scan with OpenMP + torch CPU)"},
+        "e2e": {"value": round(ips, 5), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, reasons, mx = [], set(), None
+        for ln in self.f.read().splitlines():
+            parts = [s.strip() for s in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            sm.sort()
+            # median of the samples taken under load (upper half of the distribution)
+            load = sm[len(sm) // 2:]
+            out.update(sm_mhz=load[len(load) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------ roofline instrumentation
+def scan_algo_bytes(kind, batch, H, W, D, N):
+    """Algorithmic bytes of one scan call in the reference's op-level formulation:
+    4·(3·B·KD·L + 2·B·K·N·L) + 4·(KD·N + 2·KD): u, delta, B, C read once, out written once, A/D/bias."""
+    from sigma_b200 import _lib
+    if kind == _lib.DIRS_CROSS4:
+        K, L, Bn = 4, H * W, batch
+    elif kind == _lib.DIRS_SEQ2:
+        K, L, Bn = 2, 2 * H * W, batch
+    else:  # CROSS: batch = 2 x images, each an independent K=1 scan
+        K, L, Bn = 1, H * W, batch
+    KD = K * D
+    return 4 * (3 * Bn * KD * L + 2 * Bn * K * N * L) + 4 * (KD * N + 2 * KD)
+
+
+def measure_roofline(model, rgb, mx, passes=3):
+    """Eager (un-graphed) passes with CUDA events around every fused-scan call on the launching stream."""
+    from sigma_b200 import fused
+    rec = []
+    orig = fused.ss2d_scan
+
+    def timed(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = orig(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp)
+        e1.record()
+        rec.append((scan_algo_bytes(kind, batch, H, W, D, N), N, e0, e1))
+        return y
+
+    fused.ss2d_scan = timed
+    try:
+        with torch.no_grad():
+            model(rgb, mx)          # warm
+            torch.cuda.synchronize()
+            rec.clear()
+            for _ in range(passes):
+                model(rgb, mx)
+            torch.cuda.synchronize()
+    finally:
+        fused.ss2d_scan = orig
+    tot_b = sum(r[0] for r in rec)
+    tot_ms = sum(r[2].elapsed_time(r[3]) for r in rec)
+    by_n = {}
+    for b, n, e0, e1 in rec:
+        s = by_n.setdefault(n, [0, 0.0, 0])
+        s[0] += b
+        s[1] += e0.elapsed_time(e1)
+        s[2] += 1
+    return tot_b, tot_ms, len(rec), passes, by_n
+
+
+# ------------------------------------------------------------------ main arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from sigma_b200 import _lib, modules as M
+    # dense projections run on the tensor cores in TF32 (fp32 storage, fp32 accumulate); the scan is fp32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(0)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.EncoderDecoder(cfg_of(a), criterion=None).to(dev).eval()
+    B = a.batch
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    rgb = torch.randn(B, 3, a.height, a.width, device=dev, generator=g)
+    mx = torch.randn(B, 3, a.height, a.width, device=dev, generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (eager) + launch count of one step
+    with torch.no_grad():
+        model(rgb, mx)
+        torch.cuda.synchronize()
+        n0 = _lib.launch_count()
+        out = model(rgb, mx)
+        torch.cuda.synchronize()
+        launches_per_step = _lib.launch_count() - n0
+
+    # ---- CUDA graph of one step
+    graph = None
+    static_out = out
+    if not a.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side), torch.no_grad():
+                model(rgb, mx)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph), torch.no_grad():
+                static_out = model(rgb, mx)
+        except Exception as e:  # report, fall back to eager launches (still our kernels)
+            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def step():
+        nonlocal static_out
+        if graph is not None:
+            graph.replay()
+        else:
+            with torch.no_grad():
+                static_out = model(rgb, mx)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region 1: resident inputs
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    barrier()
+    for e0, e1 in ev:
+        flush.zero_()            # L2 flush between timed iterations (outside the events)
+        e0.record()
+        step()
+        e1.record()
+    barrier()
+    total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+
+    # ---- timed region 2: end to end through the public call, host buffers
+    h_rgb = torch.randn(B, 3, a.height, a.width).pin_memory()
+    h_mx = torch.randn(B, 3, a.height, a.width).pin_memory()
+    h_out = torch.empty(tuple(static_out.shape), dtype=static_out.dtype).pin_memory()
+    def e2e_step():
+        rgb.copy_(h_rgb, non_blocking=True)
+        mx.copy_(h_mx, non_blocking=True)
+        step()
+        h_out.copy_(static_out, non_blocking=True)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    for _ in range(a.steps):
+        e2e_step()
+    s1.record()
+    barrier()
+    t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item())
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (fused SS2D scan), measured live with CUDA events
+    tot_b, tot_ms, ncalls, passes, by_n = measure_roofline(model, rgb, mx)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = tot_b / (tot_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "ss2d_scan_kernel (fused 4/2/1-direction selective scan)",
+                "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "traffic": traffic, "calls_per_step": ncalls // passes,
+                "algorithmic_bytes_per_step": tot_b // passes, "scan_ms_per_step": round(tot_ms / passes, 3),
+                "by_dstate": {str(n): {"GBps": round(v[0] / (v[1] * 1e-3) / 1e9, 1), "ms_per_step": round(v[1] / passes, 3),
+                                       "calls": v[2] // passes} for n, v in sorted(by_n.items())}}
+
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ips, dt = cpu_reference_images_per_s(a, a.cpu_sample_images)
+        cpu = {"value": round(ips, 5), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"{a.cpu_sample_images} images {a.height}x{a.width} one at a time ({dt:.1f} s): oracle port of the "
+                         "reference CPU path (C selective scan with OpenMP + torch CPU dense ops)"}
+
+    n_img = B * world * a.steps
+    in_bytes = 2 * B * 3 * a.height * a.width * 4
+    out_bytes = static_out.numel() * static_out.element_size()
+    line = {
+        "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(n_img / (total_ms * 1e-3), 3), "unit": "images/s",
+        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(total_ms / a.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"replicas x{world} (no data-path collective)", "scan_math": "fp32",
+                   "dense_math": "tf32 tensor cores, fp32 accumulate", "cuda_graph": graph is not None,
+                   "l2": "256 MiB flush between timed steps"},
+        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": round(n_img / (e2e_ms * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": out_bytes},
+        "gpu_launches": int(launches_per_step) * a.steps,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
