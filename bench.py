@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=8, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--impl", default="sigma", choices=["sigma", "reference"])
     ap.add_argument("--model", default="sigma_tiny")
     ap.add_argument("--height", type=int, default=480)
@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--num-classes", type=int, default=9)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-images", type=int, default=3)
+    ap.add_argument("--cpu-sample-images", type=int, default=2)
     return ap.parse_args()
 
 
@@ -57,6 +57,16 @@ def workload_name(a):
 
 
 # ------------------------------------------------------------------ CPU reference arm / cpu_baseline
+def cpu_threads():
+    """Threads used by the CPU arm.  The dense part is many small torch ops whose intra-op parallelism stops
+    scaling (and on a 128-core host regresses badly) beyond a few tens of threads; the C selective scan
+    (OpenMP over batch x channels) uses the same count."""
+    n = min(os.cpu_count() or 1, 32)
+    torch.set_num_threads(n)
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
 def cpu_reference_images_per_s(a, n_images, quiet=True):
     """The oracle port of the reference's CPU path (oracle/sigma_ref.py + oracle/selective_scan_ref.c:
     torch-CPU dense ops, multi-threaded C selective scan), one image at a time as engine/evaluator.py does."""
@@ -85,8 +95,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = cpu_threads()
     for _ in range(min(a.warmup, 1)):
         cpu_reference_images_per_s(a, 1)
     n = max(1, a.steps)
@@ -350,8 +359,7 @@ def main():
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
+        cores = cpu_threads()
         ips, dt = cpu_reference_images_per_s(a, a.cpu_sample_images)
         cpu = {"value": round(ips, 5), "unit": "images/s", "cores": cores, "kind": "port",
                "sample": f"{a.cpu_sample_images} images {a.height}x{a.width} one at a time ({dt:.1f} s): oracle port of the "

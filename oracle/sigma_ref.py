@@ -22,7 +22,8 @@ def selective_scan(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=Fa
     """selective_scan_interface.py:86-131 (selective_scan_ref), via the C oracle."""
     out = scan_oracle.scan_fwd(u.numpy(), delta.numpy(), A.numpy(), B.numpy(), C.numpy(),
                                None if D is None else D.numpy(),
-                               None if delta_bias is None else delta_bias.numpy(), delta_softplus)
+                               None if delta_bias is None else delta_bias.numpy(), delta_softplus,
+                               nthreads=torch.get_num_threads())
     return torch.from_numpy(out)
 
 

@@ -7,99 +7,90 @@
 //   softplus -> selective scan (state in registers, one MUFU.EX2 per element) -> D skip -> store at the
 //   POSITION the value belongs to (so CrossMerge's un-flip / un-transpose disappear).
 //
-// CTA = (channel tile DT, direction k [x L-segment], image b).  Tiles of LT scan positions are staged
-// HBM -> shared by TMA (cp.async.bulk.tensor, mbarrier complete_tx) through an NST-deep ring; the y tile
-// goes back shared -> HBM by TMA store.  Per group of 4 positions the delta' of the NEXT group is computed
-// while the recurrence of the current one runs (software pipelining: the only serial dependency is the
-// fma h = a·h + b), and all 4·SPT exponentials of a group are independent of h.
+// Mapping: ONE THREAD = ONE CHANNEL with all N states in registers; a warp = 32 consecutive channels, so
+// every shared/global access of a warp is one coalesced 128-byte row and B/C/dt_r are broadcast reads.
+// No shuffles, no redundant work: per (channel, position) the cost is N x (FMUL, MUFU.EX2, FMUL, FFMA, FFMA)
+// + R FFMA (dt_proj) + softplus — below the MUFU bound of 16 ex2/clk/SM in issue slots (the first version of
+// this kernel used 4 lanes per channel and was issue-bound: profiles/r01_launches_b8_v1.txt).
+// CTA = (channel tile DT = blockDim.x, direction k [x L-segment], image b).  Tiles of LT scan positions are
+// staged HBM -> shared by TMA (cp.async.bulk.tensor + mbarrier complete_tx) through an NST-deep ring; y goes
+// straight from registers to HBM (a warp writes 32 consecutive channels of one position = one 128-byte row).
+// Per group of 4 positions the delta' of the NEXT group is computed while the recurrence of the current one
+// runs (software pipelining: the only serial dependency is the fma h = a·h + b).
 #pragma once
 #include "scan_core.cuh"
 #include "tma.cuh"
 
 namespace sigma {
 
-template <int LPC>
+template <int N>
 struct Ss2dCfg {
-  static constexpr int NW = LPC >= 4 ? 8 : (LPC == 2 ? 8 : 4);  // warps per CTA
-  static constexpr int LT = LPC >= 2 ? 32 : 16;                 // scan positions per tile
-  static constexpr int NST = 3;                                 // TMA ring depth
-  static constexpr int CPW = 32 / LPC;
-  static constexpr int DT = NW * CPW;                           // channels per CTA: 64 / 128 / 128
-  static constexpr int NTHREADS = NW * 32;
+  static constexpr int LT = N >= 16 ? 16 : 32;   // scan positions per tile
+  static constexpr int NST = N >= 16 ? 4 : 3;    // TMA ring depth
 };
 
 struct alignas(64) Ss2dParams {
-  CUtensorMap m_xc[4], m_dbl[4], m_y[4];
+  CUtensorMap m_xc[4], m_dbl[4];
   const float *dtw, *dtb, *A, *Ds;
-  float *carry;
-  int D, N, R, Cp, kind, batch;
+  float *y, *carry;
+  int D, N, R, Cp, kind, batch, ndir;
+  long long Lseq;
   int I[4], O[4], rev[4];
+  long long istride[4], ostride[4];   // y element strides of the inner / outer walk index
   int nsplit, tiles_per_split;
 };
 
 __host__ __device__ inline size_t ss2d_smem_bytes(int LT, int DT, int NST, int Cp, bool cross) {
   const size_t stage = (size_t)LT * DT + (size_t)LT * Cp * (cross ? 2 : 1);
-  return (NST * stage + 2 * (size_t)LT * DT) * sizeof(float) + 64 /*barriers*/ + 128 /*alignment slack*/;
+  return NST * stage * sizeof(float) + 128 /*barriers*/;
 }
 
-template <int SPT, int LPC, int RP>
+template <int N, int RP>
 struct Ss2dThread {
-  float h[SPT], a2[SPT], W[RP];
+  float h[N], a2[N], W[RP];
   float bias, Dv, sumdl;
-  int lane, q, ch;
+  int ch;
+  bool ok;
 };
 
-// delta' for the 4 positions of group j (tile rows 4j..4j+3) + their u values.
-template <int SPT, int LPC, int RP, int DT>
-__device__ __forceinline__ void group_prologue(const Ss2dThread<SPT, LPC, RP> &t, const float *sXC, const float *sDB,
-                                               int Cp, int j, float (&dl)[4], float (&u)[4]) {
-  constexpr int N = SPT * LPC;
-  constexpr int PPL = LPC >= 4 ? 1 : 4 / LPC;  // positions whose delta this lane evaluates
-  const int first = LPC >= 4 ? (t.q & 3) : t.q * PPL;
-  float own[PPL];
+// delta' and u for the 4 positions of group j (tile rows 4j..4j+3)
+template <int N, int RP>
+__device__ __forceinline__ void group_prologue(const Ss2dThread<N, RP> &t, const float *sXC, const float *sDB, int DT,
+                                               int j, float (&dl)[4], float (&u)[4]) {
+  constexpr int Cp = 2 * N + RP;  // x_dbl row length: [B | C | dt_r padded to RP] (sigma_ss2d_padded_cp)
 #pragma unroll
-  for (int e = 0; e < PPL; ++e) {
-    const float *row = sDB + (4 * j + first + e) * Cp + 2 * N;
+  for (int e = 0; e < 4; ++e) {
+    const float *row = sDB + (4 * j + e) * Cp + 2 * N;
     float acc = t.bias;
 #pragma unroll
     for (int c = 0; c < RP / 4; ++c) {
-      const float4 v = *reinterpret_cast<const float4 *>(row + 4 * c);
+      const float4 v = *reinterpret_cast<const float4 *>(row + 4 * c);   // broadcast read
       acc = fmaf(t.W[4 * c + 0], v.x, acc);
       acc = fmaf(t.W[4 * c + 1], v.y, acc);
       acc = fmaf(t.W[4 * c + 2], v.z, acc);
       acc = fmaf(t.W[4 * c + 3], v.w, acc);
     }
-    own[e] = softplus20(acc);
+    dl[e] = softplus20(acc);
+    u[e] = sXC[(4 * j + e) * DT + t.ch];
   }
-  if (LPC == 1) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dl[i] = own[i % PPL];
-  } else {
-    const int base = t.lane & ~(LPC - 1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-      dl[i] = __shfl_sync(0xffffffffu, own[i % PPL], base + (LPC >= 4 ? i : i / PPL));
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) u[i] = sXC[(4 * j + i) * DT + t.ch];
 }
 
-// recurrence over `cnt` (<= 4) positions of group j, in walk order (REV: descending tile rows).
-template <int SPT, int LPC, int RP, int DT, bool WITH_Y, bool REV, bool FULL>
-__device__ __forceinline__ void group_body(Ss2dThread<SPT, LPC, RP> &t, const float *sDB, const float *sDC, float *sY,
-                                           int Cp, int j, const float (&dl)[4], const float (&u)[4], int cnt) {
-  constexpr int N = SPT * LPC;
-  float y[4] = {0.f, 0.f, 0.f, 0.f};
+// recurrence over `cnt` (<= 4) positions of group j, in walk order (REV: descending tile rows)
+template <int N, int RP, bool WITH_Y, bool REV, bool FULL>
+__device__ __forceinline__ void group_body(Ss2dThread<N, RP> &t, const float *sDB, const float *sDC, float *yrow,
+                                           long long ystride, int j, const float (&dl)[4], const float (&u)[4],
+                                           int cnt) {
+  constexpr int Cp = 2 * N + RP;
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
     const int i = REV ? 3 - ii : ii;
     if (FULL || i < cnt) {
-      float Bs[SPT], Cs[SPT];
-      const float *rb = sDB + (4 * j + i) * Cp + t.q * SPT;
-      const float *rc = sDC + (4 * j + i) * Cp + N + t.q * SPT;
+      float Bs[N], Cs[N];
+      const float *rb = sDB + (4 * j + i) * Cp;
+      const float *rc = sDC + (4 * j + i) * Cp + N;
 #pragma unroll
-      for (int s4 = 0; s4 < SPT / 4; ++s4) {
-        const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);
+      for (int s4 = 0; s4 < N / 4; ++s4) {
+        const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);   // broadcast reads
         Bs[4 * s4] = bv.x; Bs[4 * s4 + 1] = bv.y; Bs[4 * s4 + 2] = bv.z; Bs[4 * s4 + 3] = bv.w;
         if (WITH_Y) {
           const float4 cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
@@ -108,76 +99,68 @@ __device__ __forceinline__ void group_body(Ss2dThread<SPT, LPC, RP> &t, const fl
           Cs[4 * s4] = Cs[4 * s4 + 1] = Cs[4 * s4 + 2] = Cs[4 * s4 + 3] = 0.f;
         }
       }
-      scan_step<SPT, WITH_Y>(t.h, t.a2, dl[i], u[i], Bs, Cs, y[i]);
-      if (!WITH_Y) t.sumdl += dl[i];
-    }
-  }
-  if (WITH_Y) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) y[i] = channel_reduce<LPC>(y[i]);
-    if (t.q == 0) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (FULL || i < cnt) sY[(4 * j + i) * DT + t.ch] = fmaf(t.Dv, u[i], y[i]);
+      float y = 0.f;
+      scan_step<N, WITH_Y>(t.h, t.a2, dl[i], u[i], Bs, Cs, y);
+      if (WITH_Y) {
+        if (t.ok) yrow[(long long)(4 * j + i) * ystride] = fmaf(t.Dv, u[i], y);
+      } else {
+        t.sumdl += dl[i];
+      }
     }
   }
 }
 
-template <int SPT, int LPC, int RP, int DT, bool WITH_Y, bool REV>
-__device__ __forceinline__ void scan_tile(Ss2dThread<SPT, LPC, RP> &t, const float *sXC, const float *sDB,
-                                          const float *sDC, float *sY, int Cp, int npos) {
+template <int N, int RP, bool WITH_Y, bool REV>
+__device__ __forceinline__ void scan_tile(Ss2dThread<N, RP> &t, const float *sXC, const float *sDB, const float *sDC,
+                                          float *yrow, long long ystride, int DT, int npos) {
   const int nfull = npos >> 2, rem = npos & 3;
   float dl[4], u[4];
   if (REV && rem) {  // the ragged group comes first when walking backwards
-    group_prologue<SPT, LPC, RP, DT>(t, sXC, sDB, Cp, nfull, dl, u);
-    group_body<SPT, LPC, RP, DT, WITH_Y, REV, false>(t, sDB, sDC, sY, Cp, nfull, dl, u, rem);
+    group_prologue<N, RP>(t, sXC, sDB, DT, nfull, dl, u);
+    group_body<N, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
   }
   if (nfull > 0) {
     int j = REV ? nfull - 1 : 0;
-    group_prologue<SPT, LPC, RP, DT>(t, sXC, sDB, Cp, j, dl, u);
+    group_prologue<N, RP>(t, sXC, sDB, DT, j, dl, u);
 #pragma unroll 1
     for (int g = 0; g < nfull; ++g) {
       // next group's delta'/u first (clamped index: the last iteration recomputes a valid group, unused),
-      // so its loads / softplus / shuffles overlap this group's exponentials and fma chain
+      // so its loads / dot products / softplus overlap this group's exponentials and fma chains
       const int jn = REV ? max(j - 1, 0) : min(j + 1, nfull - 1);
       float dln[4], un[4];
-      group_prologue<SPT, LPC, RP, DT>(t, sXC, sDB, Cp, jn, dln, un);
-      group_body<SPT, LPC, RP, DT, WITH_Y, REV, true>(t, sDB, sDC, sY, Cp, j, dl, u, 4);
+      group_prologue<N, RP>(t, sXC, sDB, DT, jn, dln, un);
+      group_body<N, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, j, dl, u, 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { dl[i] = dln[i]; u[i] = un[i]; }
       j = REV ? j - 1 : j + 1;
     }
   }
   if (!REV && rem) {
-    group_prologue<SPT, LPC, RP, DT>(t, sXC, sDB, Cp, nfull, dl, u);
-    group_body<SPT, LPC, RP, DT, WITH_Y, REV, false>(t, sDB, sDC, sY, Cp, nfull, dl, u, rem);
+    group_prologue<N, RP>(t, sXC, sDB, DT, nfull, dl, u);
+    group_body<N, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
   }
 }
 
-template <int SPT, int LPC, int RP, int MODE>
-__global__ void __launch_bounds__(Ss2dCfg<LPC>::NTHREADS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
-  using Cfg = Ss2dCfg<LPC>;
-  constexpr int DT = Cfg::DT, LT = Cfg::LT, NST = Cfg::NST, CPW = Cfg::CPW;
-  constexpr int N = SPT * LPC;
+template <int N, int RP, int MODE>
+__global__ void __launch_bounds__(256) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+  constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // TMA destinations need 128-byte alignment
   float *stages = reinterpret_cast<float *>(smem_raw);
-  const int Cp = p.Cp;
+  const int DT = blockDim.x;
+  constexpr int Cp = 2 * N + RP;  // == p.Cp (checked on the host)
   const bool cross = p.kind == SIGMA_DIRS_CROSS;
   const int xc_fl = LT * DT, dbl_fl = LT * Cp;
   const int stage_fl = xc_fl + dbl_fl * (cross ? 2 : 1);
-  float *sYbase = stages + NST * stage_fl;
-  uint64_t *full = reinterpret_cast<uint64_t *>(sYbase + 2 * xc_fl);
+  uint64_t *full = reinterpret_cast<uint64_t *>(stages + NST * stage_fl);
 
   const int tid = threadIdx.x;
-  Ss2dThread<SPT, LPC, RP> t;
-  t.lane = tid & 31;
-  t.q = t.lane % LPC;
-  t.ch = (tid >> 5) * CPW + t.lane / LPC;
+  Ss2dThread<N, RP> t;
+  t.ch = tid;
   const int d0 = blockIdx.x * DT;
-  const int d = d0 + t.ch;
-  const bool ch_ok = d < p.D;
+  const int d = d0 + tid;
+  t.ok = d < p.D;
   const int k = cross ? 0 : blockIdx.y / p.nsplit;
   const int split = cross ? blockIdx.y : blockIdx.y - k * p.nsplit;
   const int b = blockIdx.z;
@@ -189,31 +172,31 @@ __global__ void __launch_bounds__(Ss2dCfg<LPC>::NTHREADS) ss2d_scan_kernel(const
   const int TPO = (I + LT - 1) / LT, ntiles = O * TPO;
   const int t0 = split * p.tiles_per_split, t1 = min(ntiles, t0 + p.tiles_per_split);
 
-  const long long wd = (long long)kw * p.D + (ch_ok ? d : 0);
+  const long long wd = (long long)kw * p.D + (t.ok ? d : 0);
 #pragma unroll
-  for (int s = 0; s < SPT; ++s) {
-    t.a2[s] = ch_ok ? p.A[wd * N + t.q * SPT + s] * kLog2e : 0.f;
+  for (int s = 0; s < N; ++s) {
+    t.a2[s] = t.ok ? p.A[wd * N + s] * kLog2e : 0.f;
     t.h[s] = 0.f;
   }
 #pragma unroll
-  for (int r = 0; r < RP; ++r) t.W[r] = (ch_ok && r < p.R) ? p.dtw[wd * p.R + r] : 0.f;
-  t.bias = ch_ok ? p.dtb[wd] : 0.f;
-  t.Dv = ch_ok ? p.Ds[wd] : 0.f;
+  for (int r = 0; r < RP; ++r) t.W[r] = (t.ok && r < p.R) ? p.dtw[wd * p.R + r] : 0.f;
+  t.bias = t.ok ? p.dtb[wd] : 0.f;
+  t.Dv = t.ok ? p.Ds[wd] : 0.f;
   t.sumdl = 0.f;
   float *carry_row = nullptr;
   if (MODE != MODE_SERIAL) {
-    const int ndir = cross ? 1 : (int)(gridDim.y / p.nsplit);
-    carry_row = p.carry + ((((long long)b * ndir + k) * p.D + (ch_ok ? d : 0)) * p.nsplit + split) * 2 * N;
-    if (MODE == MODE_APPLY && ch_ok) {
+    carry_row = p.carry + ((((long long)b * p.ndir + k) * p.D + (t.ok ? d : 0)) * p.nsplit + split) * 2 * N;
+    if (MODE == MODE_APPLY && t.ok) {
 #pragma unroll
-      for (int s = 0; s < SPT; ++s) t.h[s] = carry_row[N + t.q * SPT + s];
+      for (int s = 0; s < N; ++s) t.h[s] = carry_row[N + s];
     }
   }
+  float *ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + (t.ok ? d : 0);
+  const long long istride = p.istride[k], ostride = p.ostride[k];
 
   if (tid == 0) {
     tma_prefetch_desc(&p.m_xc[k]);
     tma_prefetch_desc(&p.m_dbl[k]);
-    if (WITH_Y) tma_prefetch_desc(&p.m_y[k]);
     for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
     fence_mbar_init();
   }
@@ -248,37 +231,28 @@ __global__ void __launch_bounds__(Ss2dCfg<LPC>::NTHREADS) ss2d_scan_kernel(const
     const float *sXC = stages + st * stage_fl;
     const float *sDB = sXC + xc_fl;
     const float *sDC = cross ? sDB + dbl_fl : sDB;
-    float *sY = sYbase + (it & 1) * xc_fl;
     int o, i0;
     tile_coord(tau, o, i0);
     const int npos = min(LT, I - i0);
+    float *yrow = ybase + (long long)o * ostride + (long long)i0 * istride;
 
-    if (rev) scan_tile<SPT, LPC, RP, DT, WITH_Y, true>(t, sXC, sDB, sDC, sY, Cp, npos);
-    else     scan_tile<SPT, LPC, RP, DT, WITH_Y, false>(t, sXC, sDB, sDC, sY, Cp, npos);
+    if (rev) scan_tile<N, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
+    else     scan_tile<N, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
 
-    if (WITH_Y) {
-      fence_proxy_async();                      // my y-tile writes -> visible to the TMA store
-      if (tid == 0) tma_store_wait_read<0>();   // store of tile tau-1 has finished reading the other y buffer
-    }
-    __syncthreads();                            // everyone done with input stage st and with this y tile
-    if (WITH_Y && tid == 0) {
-      tma_store_4d(&p.m_y[k], sY, d0, i0, o, b);
-      tma_store_commit();
-    }
+    __syncthreads();  // every thread is done with input stage st before it is refilled
   }
-  if (WITH_Y && tid == 0) tma_store_wait_all<0>();
 
-  if (MODE == MODE_SUMMARY && ch_ok) {
+  if (MODE == MODE_SUMMARY && t.ok) {
 #pragma unroll
-    for (int s = 0; s < SPT; ++s) {
-      carry_row[t.q * SPT + s] = ex2(t.a2[s] * t.sumdl);
-      carry_row[N + t.q * SPT + s] = t.h[s];
+    for (int s = 0; s < N; ++s) {
+      carry_row[s] = ex2(t.a2[s] * t.sumdl);
+      carry_row[N + s] = t.h[s];
     }
   }
 }
 
 // host-side launcher for one (N, RP) instantiation; defined per RP in ss2d_scan_rp*.cu
-template <int SPT, int LPC, int RP>
-int ss2d_launch(const Ss2dParams &p, int ndir, cudaStream_t stream);
+template <int N, int RP>
+int ss2d_launch(const Ss2dParams &p, int nthreads, cudaStream_t stream);
 
 }  // namespace sigma

@@ -53,26 +53,33 @@ static int pad_rp(int R) {
   return -1;
 }
 
-template <int SPT, int LPC>
-static int dispatch_rp(const Ss2dParams &p, int ndir, cudaStream_t s) {
+template <int N>
+static int dispatch_rp(const Ss2dParams &p, int nthreads, cudaStream_t s) {
   switch (pad_rp(p.R)) {
-    case 4: return ss2d_launch<SPT, LPC, 4>(p, ndir, s);
-    case 8: return ss2d_launch<SPT, LPC, 8>(p, ndir, s);
-    case 12: return ss2d_launch<SPT, LPC, 12>(p, ndir, s);
-    case 16: return ss2d_launch<SPT, LPC, 16>(p, ndir, s);
-    case 24: return ss2d_launch<SPT, LPC, 24>(p, ndir, s);
-    case 32: return ss2d_launch<SPT, LPC, 32>(p, ndir, s);
-    case 48: return ss2d_launch<SPT, LPC, 48>(p, ndir, s);
-    case 64: return ss2d_launch<SPT, LPC, 64>(p, ndir, s);
+    case 4: return ss2d_launch<N, 4>(p, nthreads, s);
+    case 8: return ss2d_launch<N, 8>(p, nthreads, s);
+    case 12: return ss2d_launch<N, 12>(p, nthreads, s);
+    case 16: return ss2d_launch<N, 16>(p, nthreads, s);
+    case 24: return ss2d_launch<N, 24>(p, nthreads, s);
+    case 32: return ss2d_launch<N, 32>(p, nthreads, s);
+    case 48: return ss2d_launch<N, 48>(p, nthreads, s);
+    case 64: return ss2d_launch<N, 64>(p, nthreads, s);
   }
   set_error("sigma_ss2d_scan_fwd: dt_rank %d > 64 unsupported", p.R);
   return SIGMA_EUNSUPPORTED;
 }
 
 static int kind_dirs(int kind) { return kind == SIGMA_DIRS_CROSS4 ? 4 : (kind == SIGMA_DIRS_SEQ2 ? 2 : 1); }
-static int lt_for(int N) { return N >= 8 ? Ss2dCfg<4>::LT : Ss2dCfg<1>::LT; }
-static int dt_for(int N) { return N == 16 ? Ss2dCfg<4>::DT : (N == 8 ? Ss2dCfg<2>::DT : Ss2dCfg<1>::DT); }
-static int nw_for(int N) { return N == 16 ? Ss2dCfg<4>::NW : (N == 8 ? Ss2dCfg<2>::NW : Ss2dCfg<1>::NW); }
+static int lt_for(int N) { return N >= 16 ? Ss2dCfg<16>::LT : Ss2dCfg<4>::LT; }
+
+// warps per CTA: the largest count <= 8 whose channel tile (32 per warp) divides D; ragged D falls back to
+// ceil(D/32) warps with a partially filled last CTA (TMA zero-fills, stores are predicated)
+static int pick_warps(int D) {
+  const int opts[] = {8, 6, 4, 3, 2, 1};
+  for (int w : opts)
+    if (D % (32 * w) == 0) return w;
+  return std::min(8, (D + 31) / 32);
+}
 
 constexpr int kMaxSplit = 32;
 
@@ -85,12 +92,15 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
                   size_t ws_bytes, int force_split, cudaStream_t stream) {
   Ss2dParams p;
   memset(&p, 0, sizeof(p));
-  p.dtw = dtw; p.dtb = dtb; p.A = A; p.Ds = Ds; p.carry = (float *)ws;
+  p.dtw = dtw; p.dtb = dtb; p.A = A; p.Ds = Ds; p.y = y; p.carry = (float *)ws;
   p.D = D; p.N = N; p.R = R; p.Cp = Cp; p.kind = kind; p.batch = batch;
   const int ndir = kind_dirs(kind);
+  p.ndir = ndir;
   const int K = kind == SIGMA_DIRS_CROSS ? 1 : ndir;        // x_dbl rows per position
   const long long Lseq = kind == SIGMA_DIRS_SEQ2 ? 2LL * H * W : (long long)H * W;
-  const int LT = lt_for(N), DT = dt_for(N);
+  p.Lseq = Lseq;
+  const int LT = lt_for(N);
+  const int NW = pick_warps(D), DT = 32 * NW;
   int rc;
   int max_tiles = 0;
   for (int k = 0; k < ndir; ++k) {
@@ -101,15 +111,16 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
     // channels-last activations (batch, Lseq, D)
     if (!colmajor) {
       p.I[k] = (int)Lseq; p.O[k] = 1;
+      p.istride[k] = D; p.ostride[k] = 0;
       dims[0] = D; dims[1] = Lseq; dims[2] = 1; dims[3] = batch;
       str[0] = (uint64_t)D * 4; str[1] = (uint64_t)Lseq * D * 4; str[2] = (uint64_t)Lseq * D * 4;
     } else {  // walk h (inner) at fixed w (outer): l1 = w·H + h  <->  position h·W + w   (vmamba.py:87)
       p.I[k] = H; p.O[k] = W;
+      p.istride[k] = (long long)W * D; p.ostride[k] = D;
       dims[0] = D; dims[1] = H; dims[2] = W; dims[3] = batch;
       str[0] = (uint64_t)W * D * 4; str[1] = (uint64_t)D * 4; str[2] = (uint64_t)Lseq * D * 4;
     }
     if ((rc = make_tmap_f32_4d(&p.m_xc[k], xc, dims, str, box))) return rc;
-    if ((rc = make_tmap_f32_4d(&p.m_y[k], y + (long long)k * batch * Lseq * D, dims, str, box))) return rc;
     // x_dbl (batch, Lseq, K, Cp): direction k's row starts at column k·Cp
     uint32_t boxd[4] = {(uint32_t)Cp, (uint32_t)LT, 1, 1};
     dims[0] = Cp;
@@ -120,12 +131,14 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
       return rc;
     max_tiles = std::max(max_tiles, p.O[k] * ((p.I[k] + LT - 1) / LT));
   }
-  // L-segments: only when the unsplit grid cannot fill the machine (each split doubles the exp work)
+  // L-segments: only when the unsplit grid cannot give every SM sub-partition (148 x 4) work.  Each split
+  // repeats the exponentials (MODE_SUMMARY), which is what bounds the d_state=16 scans, so those are split
+  // only up to one warp per sub-partition; the d_state<=8 scans (HBM-bound) up to two.
   const long long ctas = (long long)((D + DT - 1) / DT) * ndir * batch;
-  const long long warps = ctas * nw_for(N);
+  const long long warps = ctas * NW;
+  const long long want = 148LL * 4 * (N >= 16 ? 1 : 2);
   int nsplit = 1;
-  const long long target = 148LL * 16;
-  if (warps * 2 <= target) nsplit = (int)std::min<long long>((target + warps - 1) / warps, kMaxSplit);
+  if (warps < want) nsplit = (int)std::min<long long>((want + warps - 1) / warps, kMaxSplit);
   if (force_split > 0) nsplit = std::min(force_split, kMaxSplit);
   if (ws == nullptr || ws_bytes < ss2d_scan_workspace_bytes(kind, batch, D, N)) {
     if (force_split > 1) { set_error("sigma_ss2d_scan_fwd: workspace too small for %d segments", force_split); return SIGMA_EWORKSPACE; }
@@ -137,9 +150,9 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   p.nsplit = nsplit;
 
   switch (N) {
-    case 4: return dispatch_rp<4, 1>(p, ndir, stream);
-    case 8: return dispatch_rp<4, 2>(p, ndir, stream);
-    case 16: return dispatch_rp<4, 4>(p, ndir, stream);
+    case 4: return dispatch_rp<4>(p, DT, stream);
+    case 8: return dispatch_rp<8>(p, DT, stream);
+    case 16: return dispatch_rp<16>(p, DT, stream);
   }
   set_error("sigma_ss2d_scan_fwd: d_state=%d unsupported by the fused kernel (4, 8, 16)", N);
   return SIGMA_EUNSUPPORTED;
