@@ -126,6 +126,25 @@ int sigma_merge_norm_gate_fwd(const float *y, int K, int64_t k_stride, int64_t i
                               int64_t out_batch_stride, int64_t out_row_stride, int64_t rows,
                               int64_t rows_per_batch, int D, float eps, void *stream);
 
+/* UpsampleExpand tail (MambaDecoder.py:47-49): y = LayerNorm(bilinear x2 (align_corners=False) of x); x (batch,H,W,C),
+ * y (batch,2H,2W,C).  One pass: the upsampled tensor is never materialised un-normalised.              */
+int sigma_upsample2x_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,
+                              float eps, void *stream);
+
+/* FinalUpsample_X4 tail + classifier (MambaDecoder.py:95-96, 276-279): logits = Conv1x1(LayerNorm(bilinear x2 (x))).
+ * x (batch,H,W,C); wcls (num_classes, C) = the 1x1 conv weight; logits (batch, num_classes, 2H, 2W) NCHW.   */
+int sigma_upsample2x_norm_head_fwd(const float *x, const float *w, const float *b, const float *wcls, int num_classes,
+                                   float *logits, int batch, int H, int W, int C, float eps, void *stream);
+
+/* ChannelAttention pooling (vmamba.py:1738-1739): per-slice partial sums and maxima over the L positions of each image,
+ * x (batch, L, C) channels-last -> partial (batch, nslice, 2, C) [0]=sum [1]=max (the caller finishes the tiny reduction). */
+int sigma_pool_avgmax_partial_fwd(const float *x, float *partial, int batch, int64_t L, int C, int nslice, void *stream);
+
+/* out[r,:] = a[r,:]·sa[r / rows_per_batch, :] + b[r,:]·sb[:]   (a, sa nullable: out = b·sb).  CVSSDecoderBlock residuals
+ * (vmamba.py:1801,1803) with the channel-attention scaling (vmamba.py:1741) folded in.                      */
+int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const float *sb, float *out, int64_t rows,
+                        int64_t rows_per_batch, int C, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

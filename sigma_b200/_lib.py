@@ -33,6 +33,10 @@ SIGNATURES = {
     "sigma_dwconv3x3_silu_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64] + [c_int] * 4 + [c_void_p]),
     "sigma_merge_norm_gate_fwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_void_p]),
+    "sigma_upsample2x_norm_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
+    "sigma_upsample2x_norm_head_fwd": (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
+    "sigma_pool_avgmax_partial_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
+    "sigma_scale_add_fwd": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_int, c_void_p]),
 }
 
 _lib = None

@@ -200,6 +200,11 @@ size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N);
 int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
                   const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
                   size_t ws_bytes, int force_split, cudaStream_t stream);
+int upsample2x_norm_launch(const float *in, const float *gamma, const float *beta, const float *wcls, int ncls, float *out,
+                           int B, int Hin, int Win, int C, float eps, cudaStream_t stream);
+int pool_avgmax_partial_launch(const float *x, float *partial, int B, long long L, int C, int nslice, cudaStream_t stream);
+int scale_add_launch(const float *a, const float *sa, const float *b, const float *sb, float *out, long long rows,
+                     long long rows_per_batch, int C, cudaStream_t stream);
 static bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace sigma
 
@@ -286,6 +291,38 @@ int sigma_ss2d_scan_fwd_split(int kind, const float *xc, const float *xdbl, cons
   if (rc) return rc;
   return ss2d_scan_fwd(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp, workspace, workspace_bytes, nsplit,
                        (cudaStream_t)stream);
+}
+
+int sigma_upsample2x_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,
+                              float eps, void *stream) {
+  SIGMA_CHECK_ARG(x && w && b && y, "sigma_upsample2x_norm_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "sigma_upsample2x_norm_fwd: bad sizes");
+  SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(y), "sigma_upsample2x_norm_fwd: pointers must be 16-byte aligned");
+  return upsample2x_norm_launch(x, w, b, nullptr, 0, y, batch, H, W, C, eps, (cudaStream_t)stream);
+}
+
+int sigma_upsample2x_norm_head_fwd(const float *x, const float *w, const float *b, const float *wcls, int num_classes,
+                                   float *logits, int batch, int H, int W, int C, float eps, void *stream) {
+  SIGMA_CHECK_ARG(x && w && b && wcls && logits, "sigma_upsample2x_norm_head_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && num_classes > 0,
+                  "sigma_upsample2x_norm_head_fwd: bad sizes");
+  SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(wcls), "sigma_upsample2x_norm_head_fwd: pointers must be 16-byte aligned");
+  return upsample2x_norm_launch(x, w, b, wcls, num_classes, logits, batch, H, W, C, eps, (cudaStream_t)stream);
+}
+
+int sigma_pool_avgmax_partial_fwd(const float *x, float *partial, int batch, int64_t L, int C, int nslice, void *stream) {
+  SIGMA_CHECK_ARG(x && partial, "sigma_pool_avgmax_partial_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && L > 0 && C > 0 && C % 4 == 0 && nslice > 0 && nslice <= 65535 && al16(x),
+                  "sigma_pool_avgmax_partial_fwd: bad sizes / alignment");
+  return pool_avgmax_partial_launch(x, partial, batch, L, C, nslice, (cudaStream_t)stream);
+}
+
+int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const float *sb, float *out, int64_t rows,
+                        int64_t rows_per_batch, int C, void *stream) {
+  SIGMA_CHECK_ARG(b && sb && out && (a == nullptr || sa != nullptr), "sigma_scale_add_fwd: null pointer");
+  SIGMA_CHECK_ARG(rows >= 0 && rows_per_batch > 0 && C > 0 && C % 4 == 0 && al16(a) && al16(sa) && al16(b) && al16(sb) && al16(out),
+                  "sigma_scale_add_fwd: bad sizes / alignment");
+  return scale_add_launch(a, sa, b, sb, out, rows, rows_per_batch, C, (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop

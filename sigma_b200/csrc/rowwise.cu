@@ -4,6 +4,8 @@
 //                      = CrossMerge sum + out_norm + y·SiLU(z) (vmamba.py:217-224,1077) otherwise
 //   dwconv3x3_silu   : depthwise 3x3 (pad 1) + bias + SiLU on NHWC (vmamba.py:683-692,1072)
 // All are HBM-bound; loads/stores are 16-byte, rows are contiguous in the channel dimension.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace sigma {
@@ -154,6 +156,242 @@ int dwconv3x3_silu_launch(const float *x, long long x_row_stride, long long x_ba
   if (total == 0) return SIGMA_OK;
   dim3 grid((D + DW_CH - 1) / DW_CH, (unsigned)((total + DW_POS_PER_CTA - 1) / DW_POS_PER_CTA));
   dwconv3x3_silu_kernel<<<grid, 256, 0, stream>>>(x, x_row_stride, x_batch_stride, w, bias, y, y_batch_stride, batch, H, W, D);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+}  // namespace sigma
+
+// =============================================================================================
+// Decoder tail kernels (MambaDecoder.py:33-51, 76-97, 272-280; vmamba.py:1725-1757, 1800-1805)
+// =============================================================================================
+namespace sigma {
+
+// F.interpolate(scale_factor=2, mode='bilinear', align_corners=False) source taps for output index o:
+// src = (o + 0.5)/2 - 0.5, clamped at 0 (PyTorch area_pixel_compute_source_index), i1 = min(i0+1, n-1)
+__device__ __forceinline__ void bilinear2x_taps(int o, int n, int &i0, int &i1, float &w1) {
+  float s = ((float)o + 0.5f) * 0.5f - 0.5f;
+  s = fmaxf(s, 0.f);
+  i0 = (int)s;
+  i1 = min(i0 + 1, n - 1);
+  w1 = s - (float)i0;
+}
+
+// out[b, oh, ow, :] = LayerNorm( bilinear2x(in)[b, oh, ow, :] ) — one warp per output pixel.
+// With NCLS > 0 the normalised row is additionally projected by a (NCLS, C) matrix (the decoder's final
+// 1x1 conv, MambaDecoder.py:279) and only the logits are written, in NCHW.
+template <int MAXV, int NCLS>
+__global__ void __launch_bounds__(256) upsample2x_norm_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
+                                                             const float *__restrict__ beta, const float *__restrict__ wcls,
+                                                             float *__restrict__ out, int B, int Hin, int Win, int C,
+                                                             float eps) {
+  __shared__ float slog[NCLS > 0 ? NCLS : 1][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  const long long npix = (long long)B * Ho * Wo;
+  const int PPW = NCLS > 0 ? 4 : 1;  // pixels per warp
+  const long long pix0 = ((long long)blockIdx.x * 8 + warp) * PPW;
+  const int nvec = C >> 2;
+  for (int pp = 0; pp < PPW; ++pp) {
+    const long long pix = pix0 + pp;
+    if (pix >= npix) break;
+    const int b = (int)(pix / ((long long)Ho * Wo));
+    const int rem = (int)(pix - (long long)b * Ho * Wo);
+    const int oh = rem / Wo, ow = rem - oh * Wo;
+    int h0, h1, w0, w1;
+    float fh, fw;
+    bilinear2x_taps(oh, Hin, h0, h1, fh);
+    bilinear2x_taps(ow, Win, w0, w1, fw);
+    const float c00 = (1.f - fh) * (1.f - fw), c01 = (1.f - fh) * fw, c10 = fh * (1.f - fw), c11 = fh * fw;
+    const float *base = in + (long long)b * Hin * Win * C;
+    const float4 *r00 = reinterpret_cast<const float4 *>(base + ((long long)h0 * Win + w0) * C);
+    const float4 *r01 = reinterpret_cast<const float4 *>(base + ((long long)h0 * Win + w1) * C);
+    const float4 *r10 = reinterpret_cast<const float4 *>(base + ((long long)h1 * Win + w0) * C);
+    const float4 *r11 = reinterpret_cast<const float4 *>(base + ((long long)h1 * Win + w1) * C);
+    float4 x[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int idx = lane + 32 * v;
+      x[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < nvec) {
+        const float4 a = __ldg(r00 + idx), bq = __ldg(r01 + idx), c = __ldg(r10 + idx), d = __ldg(r11 + idx);
+        // same association as PyTorch's upsample_bilinear2d: h0lambda*(w0l*a + w1l*b) + h1lambda*(w0l*c + w1l*d)
+        x[v].x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
+        x[v].y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
+        x[v].z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
+        x[v].w = (1.f - fh) * ((1.f - fw) * a.w + fw * bq.w) + fh * ((1.f - fw) * c.w + fw * d.w);
+        s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+      }
+    }
+    (void)c00; (void)c01; (void)c10; (void)c11;
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v)
+      if (lane + 32 * v < nvec) {
+        const float dx = x[v].x - mean, dy = x[v].y - mean, dz = x[v].z - mean, dw = x[v].w - mean;
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    float acc[NCLS > 0 ? NCLS : 1];
+#pragma unroll
+    for (int c = 0; c < (NCLS > 0 ? NCLS : 1); ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int v = 0; v < MAXV; ++v) {
+      const int idx = lane + 32 * v;
+      if (idx < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(gamma) + idx);
+        const float4 bt = __ldg(reinterpret_cast<const float4 *>(beta) + idx);
+        float4 o;
+        o.x = fmaf((x[v].x - mean) * rstd, g.x, bt.x);
+        o.y = fmaf((x[v].y - mean) * rstd, g.y, bt.y);
+        o.z = fmaf((x[v].z - mean) * rstd, g.z, bt.z);
+        o.w = fmaf((x[v].w - mean) * rstd, g.w, bt.w);
+        if (NCLS > 0) {
+#pragma unroll
+          for (int c = 0; c < (NCLS > 0 ? NCLS : 1); ++c) {
+            const float4 wv = __ldg(reinterpret_cast<const float4 *>(wcls + (long long)c * C) + idx);
+            acc[c] = fmaf(o.x, wv.x, fmaf(o.y, wv.y, fmaf(o.z, wv.z, fmaf(o.w, wv.w, acc[c]))));
+          }
+        } else {
+          reinterpret_cast<float4 *>(out + pix * C)[idx] = o;
+        }
+      }
+    }
+    if (NCLS > 0) {
+#pragma unroll
+      for (int c = 0; c < (NCLS > 0 ? NCLS : 1); ++c) {
+        const float v = warp_sum(acc[c]);
+        if (lane == 0) slog[c][warp * 4 + pp] = v;
+      }
+    }
+  }
+  if (NCLS > 0) {
+    __syncthreads();
+    // 32 consecutive pixels x NCLS classes -> NCHW, 128-byte runs per class
+    const long long p0 = (long long)blockIdx.x * 32;
+    const long long HWo = (long long)Ho * Wo;
+    for (int i = threadIdx.x; i < NCLS * 32; i += blockDim.x) {
+      const int c = i >> 5, j = i & 31;
+      const long long pix = p0 + j;
+      if (pix < npix) {
+        const long long b = pix / HWo, r = pix - b * HWo;
+        out[(b * NCLS + c) * HWo + r] = slog[c][j];
+      }
+    }
+  }
+}
+
+template <int NCLS>
+static int upsample2x_norm_dispatch(const float *in, const float *gamma, const float *beta, const float *wcls, float *out,
+                                    int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
+  const long long npix = 4LL * B * Hin * Win;
+  const int ppc = NCLS > 0 ? 32 : 8;
+  const unsigned grid = (unsigned)((npix + ppc - 1) / ppc);
+  const int nvec = C >> 2;
+#define LAUNCH(MV) upsample2x_norm_kernel<MV, NCLS><<<grid, 256, 0, stream>>>(in, gamma, beta, wcls, out, B, Hin, Win, C, eps)
+  if (nvec <= 32) LAUNCH(1);
+  else if (nvec <= 64) LAUNCH(2);
+  else if (nvec <= 128) LAUNCH(4);
+  else if (nvec <= 256) LAUNCH(8);
+  else { set_error("upsample2x_norm: C=%d > 1024 unsupported", C); return SIGMA_EUNSUPPORTED; }
+#undef LAUNCH
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+int upsample2x_norm_launch(const float *in, const float *gamma, const float *beta, const float *wcls, int ncls, float *out,
+                           int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
+  switch (ncls) {
+    case 0: return upsample2x_norm_dispatch<0>(in, gamma, beta, wcls, out, B, Hin, Win, C, eps, stream);
+#define CASE(n) case n: return upsample2x_norm_dispatch<n>(in, gamma, beta, wcls, out, B, Hin, Win, C, eps, stream);
+    CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10) CASE(11) CASE(12) CASE(13) CASE(14) CASE(16)
+    CASE(19) CASE(20) CASE(21) CASE(37) CASE(40) CASE(41)
+#undef CASE
+  }
+  set_error("upsample2x_norm: num_classes=%d has no fused head instantiation", ncls);
+  return SIGMA_EUNSUPPORTED;
+}
+
+// ---- channel attention pooling: per (image, channel) mean and max over H·W, channels-last ----
+// partial[b][s][0][c] = sum, partial[b][s][1][c] = max over the s-th slice of positions
+__global__ void __launch_bounds__(256) pool_avgmax_partial_kernel(const float *__restrict__ x, float *__restrict__ partial,
+                                                                 long long L, int C, int nslice) {
+  extern __shared__ float sred[];  // [2][rows][C]
+  const int b = blockIdx.y, s = blockIdx.x;
+  const int nvec = C >> 2;
+  const int rows = blockDim.x / nvec;          // position rows processed per iteration
+  const int cq = threadIdx.x % nvec, pr = threadIdx.x / nvec;
+  const long long per = (L + nslice - 1) / nslice;
+  const long long l0 = (long long)s * per, l1 = min(L, l0 + per);
+  float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  if (pr < rows) {
+    const float4 *xb = reinterpret_cast<const float4 *>(x + (long long)b * L * C) + cq;
+    for (long long l = l0 + pr; l < l1; l += rows) {
+      const float4 v = __ldg(xb + l * nvec);
+      sm.x += v.x; sm.y += v.y; sm.z += v.z; sm.w += v.w;
+      mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w);
+    }
+    float *ps = sred + (size_t)pr * C + 4 * cq;
+    float *pm = sred + (size_t)rows * C + (size_t)pr * C + 4 * cq;
+    ps[0] = sm.x; ps[1] = sm.y; ps[2] = sm.z; ps[3] = sm.w;
+    pm[0] = mx.x; pm[1] = mx.y; pm[2] = mx.z; pm[3] = mx.w;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, m = -INFINITY;
+    for (int r = 0; r < rows; ++r) {
+      a += sred[(size_t)r * C + c];
+      m = fmaxf(m, sred[(size_t)rows * C + (size_t)r * C + c]);
+    }
+    float *o = partial + (((long long)b * nslice + s) * 2) * C;
+    o[c] = a;
+    o[C + c] = m;
+  }
+}
+
+int pool_avgmax_partial_launch(const float *x, float *partial, int B, long long L, int C, int nslice, cudaStream_t stream) {
+  const int nvec = C >> 2;
+  if (nvec > 256) { set_error("pool_avgmax: C=%d > 1024 unsupported", C); return SIGMA_EUNSUPPORTED; }
+  const int rows = 256 / nvec;
+  const size_t smem = 2 * (size_t)rows * C * sizeof(float);
+  dim3 grid(nslice, B);
+  pool_avgmax_partial_kernel<<<grid, 256, smem, stream>>>(x, partial, L, C, nslice);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+// out[r,:] = a[r,:]·sa[b(r),:] + b[r,:]·sb[:]      (CVSSDecoderBlock tail: CAB·sigmoid(attn) + x·scale2, vmamba.py:1741,1803;
+// with a = NULL: out = b·sb, the x·scale1 residual of vmamba.py:1801)
+__global__ void __launch_bounds__(256) scale_add_kernel(const float4 *__restrict__ a, const float *__restrict__ sa,
+                                                       const float4 *__restrict__ bq, const float *__restrict__ sb,
+                                                       float4 *__restrict__ out, long long nvec_total, int nvec,
+                                                       long long rows_per_batch) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nvec;
+    const int c = (int)(i - r * nvec);
+    const float4 vb = __ldg(bq + i);
+    const float4 s2 = __ldg(reinterpret_cast<const float4 *>(sb) + c);
+    float4 o = make_float4(vb.x * s2.x, vb.y * s2.y, vb.z * s2.z, vb.w * s2.w);
+    if (a != nullptr) {
+      const float4 va = __ldg(a + i);
+      const float4 s1 = __ldg(reinterpret_cast<const float4 *>(sa) + (r / rows_per_batch) * nvec + c);
+      o.x = fmaf(va.x, s1.x, o.x); o.y = fmaf(va.y, s1.y, o.y); o.z = fmaf(va.z, s1.z, o.z); o.w = fmaf(va.w, s1.w, o.w);
+    }
+    out[i] = o;
+  }
+}
+
+int scale_add_launch(const float *a, const float *sa, const float *b, const float *sb, float *out, long long rows,
+                     long long rows_per_batch, int C, cudaStream_t stream) {
+  const long long tot = rows * (C >> 2);
+  if (tot == 0) return SIGMA_OK;
+  const unsigned grid = (unsigned)std::min<long long>((tot + 255) / 256, 148LL * 32);
+  scale_add_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4 *>(a), sa, reinterpret_cast<const float4 *>(b), sb,
+                                             reinterpret_cast<float4 *>(out), tot, C >> 2, rows_per_batch);
   SIGMA_CHECK_LAUNCH();
   return SIGMA_OK;
 }

@@ -222,13 +222,92 @@ def conmb_ss2d(m, x_rgb, x_e, residual=None):
     return out if residual is None else residual + out
 
 
+# ---------------------------------------------------------------- decoder pieces
+def ln_nhwc(ln, x):
+    """nn.LayerNorm over the last dim of a channels-last tensor of any rank."""
+    x = x.contiguous()
+    return layernorm(x.view(-1, x.shape[-1]), ln).view(x.shape)
+
+
+def upsample2x_norm(x, ln):
+    """LayerNorm(bilinear x2 (x)) in one pass (UpsampleExpand tail, MambaDecoder.py:47-49)."""
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().sigma_upsample2x_norm_fwd(_p(x), _p(ln.weight), _p(ln.bias), _p(y), B, H, W, C, float(ln.eps),
+                                                     _stream()), "sigma_upsample2x_norm_fwd")
+    return y
+
+
+def upsample2x_norm_head(x, ln, conv1x1):
+    """Conv1x1(LayerNorm(bilinear x2 (x))) -> NCHW logits (MambaDecoder.py:95-96,276-279)."""
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    ncls = conv1x1.weight.shape[0]
+    w = conv1x1.weight.view(ncls, C)
+    out = torch.empty((B, ncls, 2 * H, 2 * W), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().sigma_upsample2x_norm_head_fwd(_p(x), _p(ln.weight), _p(ln.bias), _p(w), ncls, _p(out), B, H, W, C,
+                                                          float(ln.eps), _stream()), "sigma_upsample2x_norm_head_fwd")
+    return out
+
+
+def pool_avgmax(t):
+    """(B, H, W, C) channels-last -> mean and max over H·W, each (B, C)."""
+    B, H, W, C = t.shape
+    L = H * W
+    nslice = max(1, min(64, L // 256))
+    part = torch.empty((B, nslice, 2, C), dtype=torch.float32, device=t.device)
+    _lib.check(_lib.lib().sigma_pool_avgmax_partial_fwd(_p(t), _p(part), B, L, C, nslice, _stream()), "sigma_pool_avgmax_partial_fwd")
+    return part[:, :, 0].sum(1) / L, part[:, :, 1].amax(1)
+
+
+def scale_add(a, sa, b, sb, rows_per_batch):
+    """a·sa[batch] + b·sb, all channels-last with C = last dim."""
+    out = torch.empty_like(b)
+    C = b.shape[-1]
+    rows = b.numel() // C
+    _lib.check(_lib.lib().sigma_scale_add_fwd(_p(a), _p(sa), _p(b), _p(sb), _p(out), rows, rows_per_batch, C, _stream()),
+               "sigma_scale_add_fwd")
+    return out
+
+
 def cvss_decoder_block(blk, x):
-    """CVSSDecoderBlock._forward (vmamba.py:1800-1805)."""
+    """CVSSDecoderBlock._forward (vmamba.py:1800-1805) with ChannelAttentionBlock (vmamba.py:1725-1757)."""
     x = x.contiguous()
     B, H, W, C = x.shape
     xn = layernorm(x.view(-1, C), blk.norm1).view(B, H, W, C)
-    x1 = ss2d(blk.op, xn, residual=x * blk.scale1)
+    x1 = ss2d(blk.op, xn, residual=scale_add(None, None, x, blk.scale1, H * W))
     xn2 = layernorm(x1.view(-1, C), blk.norm2).view(B, H, W, C)
-    t = blk.conv_blk(xn2.permute(0, 3, 1, 2))            # channels_last view: cuDNN NHWC convs, no copy
-    y = t + (x1 * blk.scale2).permute(0, 3, 1, 2)
-    return y.permute(0, 2, 3, 1).contiguous()
+    cab = blk.conv_blk.cab
+    t = cab[2](cab[1](cab[0](xn2.permute(0, 3, 1, 2))))            # conv3x3 -> GELU -> conv3x3 on a channels_last view
+    t = t.permute(0, 2, 3, 1).contiguous()                           # (B,H,W,C); no copy when cuDNN kept channels_last
+    avg, mx = pool_avgmax(t)
+    fc = cab[3].fc
+    attn = torch.sigmoid(fc(avg.view(B, C, 1, 1)) + fc(mx.view(B, C, 1, 1))).view(B, C).contiguous()
+    return scale_add(t, attn, x1, blk.scale2, H * W)               # CAB(x)·attn + x·scale2
+
+
+def patch_expand(m, x):
+    """PatchExpand (MambaDecoder.py:12-30)."""
+    B, H, W, C = x.shape
+    y = linear(x.reshape(B * H * W, C), m.expand.weight).view(B, H, W, 2, 2, C // 2)
+    y = y.permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, C // 2)
+    return ln_nhwc(m.norm, y)
+
+
+def upsample_expand(m, x):
+    """UpsampleExpand (MambaDecoder.py:33-51)."""
+    B, H, W, C = x.shape
+    y = linear(x.reshape(B * H * W, C), m.linear.weight).view(B, H, W, C // 2)
+    return upsample2x_norm(y, m.norm)
+
+
+def final_head(dec, x):
+    """MambaDecoder.up_x4 (MambaDecoder.py:272-280) = FinalUpsample_X4 (:87-97) + 1x1 conv.  linear2 is applied before
+    the first bilinear x2 instead of after it: both are linear maps over different axes (channels vs space), so
+    they commute exactly in real arithmetic and the 240x320 GEMM shrinks 4x."""
+    B, H, W, C = x.shape
+    t = linear(x.reshape(B * H * W, C), dec.up.linear1.weight)
+    t = linear(t, dec.up.linear2.weight).view(B, H, W, C)
+    t = F.interpolate(t.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    return upsample2x_norm_head(t, dec.up.norm, dec.output)

@@ -621,12 +621,20 @@ class Backbone_VSSM(VSSM):
 
     def forward_nhwc(self, x):
         """Stage outputs (after outnorm{i}) in channels-last (B,H,W,C) — used by the fused encoder."""
-        x = self.patch_embed(x)
+        fused_ln = None
+        if _fused_ok(x):
+            from . import fused
+            fused_ln = fused.ln_nhwc
+            x = self.patch_embed[0](x).permute(0, 2, 3, 1)
+            x = fused_ln(self.patch_embed[2], x) if isinstance(self.patch_embed[2], nn.LayerNorm) else x.contiguous()
+        else:
+            x = self.patch_embed(x)
         outs = []
         for i, layer in enumerate(self.layers):
             x = layer.blocks(x)
             if i in self.out_indices:
-                outs.append(getattr(self, f"outnorm{i}")(x))
+                norm = getattr(self, f"outnorm{i}")
+                outs.append(fused_ln(norm, x) if fused_ln and isinstance(norm, nn.LayerNorm) else norm(x))
             x = layer.downsample(x)
         return outs
 
@@ -712,6 +720,9 @@ class PatchExpand(nn.Module):
         self.norm = norm_layer(dim // dim_scale)
 
     def forward(self, x):
+        if _fused_ok(x) and isinstance(self.norm, nn.LayerNorm) and isinstance(self.expand, nn.Linear):
+            from . import fused
+            return fused.patch_expand(self, x)
         x = self.expand(x)
         B, H, W, C = x.shape
         x = x.view(B, H, W, 2, 2, C // 4).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, C // 4)
@@ -729,6 +740,9 @@ class UpsampleExpand(nn.Module):
         self.norm = norm_layer(dim // 2)
 
     def forward(self, x):
+        if _fused_ok(x) and isinstance(self.norm, nn.LayerNorm):
+            from . import fused
+            return fused.upsample_expand(self, x)
         return self.norm(_bilinear_nhwc(self.linear(x), scale_factor=2))
 
 
@@ -816,10 +830,17 @@ class MambaDecoder(nn.Module):
                 y = layer_up(y + skip)
             if self.deep_supervision and inx != self.num_layers - 1:
                 ups.append(self.norm_ds[inx](y))
-        x = self.norm_up(y)
+        if _fused_ok(y) and isinstance(self.norm_up, nn.LayerNorm):
+            from . import fused
+            x = fused.ln_nhwc(self.norm_up, y)
+        else:
+            x = self.norm_up(y)
         return (x, ups) if self.deep_supervision else x
 
     def up_x4(self, x, pz):
+        if _fused_ok(x) and isinstance(self.up.norm, nn.LayerNorm):
+            from . import fused
+            return fused.final_head(self, x)
         x = self.up(x)                                       # (B, 4H, 4W, C)
         return self.output(x.permute(0, 3, 1, 2))            # channels_last view; 1x1 conv = per-pixel linear
 

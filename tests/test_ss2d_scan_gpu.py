@@ -141,3 +141,38 @@ def test_merge_norm_gate():
         fused.merge_norm_gate(y.cuda(), K, B * L * D, L * D, ln.cuda(), ctypes.c_void_p(zc.data_ptr() + 4 * D), 2 * D,
                               gate.cuda(), out, L * D, D, B * L, L, D)
     assert_close(out, ref, 2e-5, 5e-5, "merge+norm+gate")
+
+
+@pytest.mark.parametrize("B,H,W,C,ncls", [(2, 5, 7, 32, 0), (1, 30, 40, 192, 0), (2, 6, 4, 96, 9), (1, 15, 20, 32, 5), (1, 3, 3, 128, 40)])
+def test_upsample2x_norm_and_head(B, H, W, C, ncls):
+    from sigma_b200 import fused
+    x = P.randn(S, f"up/{B}/{H}/{W}/{C}", (B, H, W, C))
+    ln = torch.nn.LayerNorm(C)
+    conv = torch.nn.Conv2d(C, max(ncls, 1), 1, bias=False)
+    with torch.no_grad():
+        ln.weight.copy_(P.randn(S, "up/w", (C,), 0.1, 1.0))
+        ln.bias.copy_(P.randn(S, "up/b", (C,), 0.1))
+        conv.weight.copy_(P.randn(S, "up/cw", tuple(conv.weight.shape), C ** -0.5))
+        up = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False)
+        ref = ln(up.permute(0, 2, 3, 1))
+        if ncls:
+            ref = conv(ref.permute(0, 3, 1, 2))
+            got = fused.upsample2x_norm_head(x.cuda(), ln.cuda(), conv.cuda())
+        else:
+            got = fused.upsample2x_norm(x.cuda(), ln.cuda())
+    assert_close(got, ref, 2e-5, 5e-5, f"upsample2x_norm ncls={ncls}")
+
+
+def test_pool_and_scale_add():
+    from sigma_b200 import fused
+    B, H, W, C = 2, 33, 40, 96
+    t = P.randn(S, "pool/t", (B, H, W, C))
+    avg, mx = fused.pool_avgmax(t.cuda())
+    assert_close(avg, t.mean(dim=(1, 2)), 1e-5, 1e-5, "avg pool")
+    assert_close(mx, t.amax(dim=(1, 2)), 0, 0, "max pool")
+    a, bq = P.randn(S, "sa/a", (B, H, W, C)), P.randn(S, "sa/b", (B, H, W, C))
+    sa, sb = P.rand(S, "sa/sa", (B, C)), P.randn(S, "sa/sb", (C,))
+    got = fused.scale_add(a.cuda(), sa.cuda(), bq.cuda(), sb.cuda(), H * W)
+    assert_close(got, a * sa[:, None, None, :] + bq * sb, 1e-6, 1e-6, "scale_add")
+    got = fused.scale_add(None, None, bq.cuda(), sb.cuda(), H * W)
+    assert_close(got, bq * sb, 1e-6, 1e-6, "scale only")
