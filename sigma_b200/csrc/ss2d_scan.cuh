@@ -12,9 +12,11 @@
 // No shuffles, no redundant work: per (channel, position) the cost is N x (FMUL, MUFU.EX2, FMUL, FFMA, FFMA)
 // + R FFMA (dt_proj) + softplus — below the MUFU bound of 16 ex2/clk/SM in issue slots (the first version of
 // this kernel used 4 lanes per channel and was issue-bound: profiles/r01_launches_b8_v1.txt).
-// CTA = (channel tile DT = blockDim.x, direction k [x L-segment], image b).  Tiles of LT scan positions are
-// staged HBM -> shared by TMA (cp.async.bulk.tensor + mbarrier complete_tx) through an NST-deep ring; y goes
-// straight from registers to HBM (a warp writes 32 consecutive channels of one position = one 128-byte row).
+// CTA = (channel tile DT, direction k [x L-segment], image b) = DT/32 consumer warps + one TMA producer warp.
+// Tiles of LT scan positions are staged HBM -> shared by TMA (cp.async.bulk.tensor) through an NST-deep ring
+// guarded by full/empty mbarriers, so consumer warps never wait for each other (no CTA-wide barrier in the
+// loop); y goes straight from registers to HBM (a warp writes 32 consecutive channels of one position = one
+// 128-byte row).
 // Per group of 4 positions the delta' of the NEXT group is computed while the recurrence of the current one
 // runs (software pipelining: the only serial dependency is the fma h = a·h + b).
 #pragma once
@@ -142,25 +144,29 @@ __device__ __forceinline__ void scan_tile(Ss2dThread<N, RP> &t, const float *sXC
 }
 
 template <int N, int RP, int MODE>
-__global__ void __launch_bounds__(256) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+__global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // TMA destinations need 128-byte alignment
   float *stages = reinterpret_cast<float *>(smem_raw);
-  const int DT = blockDim.x;
   constexpr int Cp = 2 * N + RP;  // == p.Cp (checked on the host)
   const bool cross = p.kind == SIGMA_DIRS_CROSS;
+
+  const int tid = threadIdx.x;
+  const int DT = blockDim.x - 32;            // consumer threads = channels; the last warp is the TMA producer
+  const int nwarps_c = DT >> 5;
+  const bool is_producer = tid >= DT;
   const int xc_fl = LT * DT, dbl_fl = LT * Cp;
   const int stage_fl = xc_fl + dbl_fl * (cross ? 2 : 1);
   uint64_t *full = reinterpret_cast<uint64_t *>(stages + NST * stage_fl);
+  uint64_t *empty = full + NST;
 
-  const int tid = threadIdx.x;
   Ss2dThread<N, RP> t;
   t.ch = tid;
   const int d0 = blockIdx.x * DT;
   const int d = d0 + tid;
-  t.ok = d < p.D;
+  t.ok = !is_producer && d < p.D;
   const int k = cross ? 0 : blockIdx.y / p.nsplit;
   const int split = cross ? blockIdx.y : blockIdx.y - k * p.nsplit;
   const int b = blockIdx.z;
@@ -172,6 +178,43 @@ __global__ void __launch_bounds__(256) ss2d_scan_kernel(const __grid_constant__ 
   const int TPO = (I + LT - 1) / LT, ntiles = O * TPO;
   const int t0 = split * p.tiles_per_split, t1 = min(ntiles, t0 + p.tiles_per_split);
 
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);           // one arrive (the producer's expect_tx) + the TMA bytes
+      mbar_init(&empty[s], nwarps_c);   // one arrive per consumer warp
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  auto tile_coord = [&](int tau, int &o, int &i0) {
+    const int tm = rev ? ntiles - 1 - tau : tau;
+    o = tm / TPO;
+    i0 = (tm - o * TPO) * LT;
+  };
+
+  if (is_producer) {
+    // ===== TMA producer warp: one elected lane refills a ring slot as soon as every consumer warp released it =====
+    if (tid == DT) {
+      tma_prefetch_desc(&p.m_xc[k]);
+      tma_prefetch_desc(&p.m_dbl[k]);
+      const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
+      for (int tau = t0; tau < t1; ++tau) {
+        const int it = tau - t0, st = it % NST;
+        mbar_wait(&empty[st], (uint32_t)(((it / NST) & 1) ^ 1));   // fresh barrier: parity 1 passes immediately
+        float *dst = stages + st * stage_fl;
+        int o, i0;
+        tile_coord(tau, o, i0);
+        mbar_arrive_expect_tx(&full[st], tx_bytes);
+        tma_load_4d(dst, &p.m_xc[k], &full[st], d0, i0, o, b);
+        tma_load_4d(dst + xc_fl, &p.m_dbl[k], &full[st], 0, i0, o, b);
+        if (cross) tma_load_4d(dst + xc_fl + dbl_fl, &p.m_dbl[k], &full[st], 0, i0, o, bC);
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps: one channel per thread =====
   const long long wd = (long long)kw * p.D + (t.ok ? d : 0);
 #pragma unroll
   for (int s = 0; s < N; ++s) {
@@ -194,38 +237,9 @@ __global__ void __launch_bounds__(256) ss2d_scan_kernel(const __grid_constant__ 
   float *ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + (t.ok ? d : 0);
   const long long istride = p.istride[k], ostride = p.ostride[k];
 
-  if (tid == 0) {
-    tma_prefetch_desc(&p.m_xc[k]);
-    tma_prefetch_desc(&p.m_dbl[k]);
-    for (int s = 0; s < NST; ++s) mbar_init(&full[s], 1);
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
-  auto tile_coord = [&](int tau, int &o, int &i0) {
-    const int tm = rev ? ntiles - 1 - tau : tau;
-    o = tm / TPO;
-    i0 = (tm - o * TPO) * LT;
-  };
-  auto issue = [&](int tau) {
-    const int st = (tau - t0) % NST;
-    float *dst = stages + st * stage_fl;
-    int o, i0;
-    tile_coord(tau, o, i0);
-    mbar_arrive_expect_tx(&full[st], tx_bytes);
-    tma_load_4d(dst, &p.m_xc[k], &full[st], d0, i0, o, b);
-    tma_load_4d(dst + xc_fl, &p.m_dbl[k], &full[st], 0, i0, o, b);
-    if (cross) tma_load_4d(dst + xc_fl + dbl_fl, &p.m_dbl[k], &full[st], 0, i0, o, bC);
-  };
-
-  if (tid == 0)
-    for (int tau = t0; tau < min(t1, t0 + NST - 1); ++tau) issue(tau);
-
   for (int tau = t0; tau < t1; ++tau) {
     const int it = tau - t0;
     const int st = it % NST;
-    if (tid == 0 && tau + NST - 1 < t1) issue(tau + NST - 1);  // slot freed by the barrier that ended iteration tau-1
     mbar_wait(&full[st], (uint32_t)((it / NST) & 1));
 
     const float *sXC = stages + st * stage_fl;
@@ -239,7 +253,8 @@ __global__ void __launch_bounds__(256) ss2d_scan_kernel(const __grid_constant__ 
     if (rev) scan_tile<N, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
     else     scan_tile<N, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
 
-    __syncthreads();  // every thread is done with input stage st before it is refilled
+    __syncwarp();
+    if ((tid & 31) == 0) mbar_arrive(&empty[st]);   // this warp is done with ring slot st
   }
 
   if (MODE == MODE_SUMMARY && t.ok) {
