@@ -7,11 +7,12 @@
 //   softplus -> selective scan (state in registers, one MUFU.EX2 per element) -> D skip -> store at the
 //   POSITION the value belongs to (so CrossMerge's un-flip / un-transpose disappear).
 //
-// Mapping: ONE THREAD = ONE CHANNEL with all N states in registers; a warp = 32 consecutive channels, so
-// every shared/global access of a warp is one coalesced 128-byte row and B/C/dt_r are broadcast reads.
-// No shuffles, no redundant work: per (channel, position) the cost is N x (FMUL, MUFU.EX2, FMUL, FFMA, FFMA)
-// + R FFMA (dt_proj) + softplus — below the MUFU bound of 16 ex2/clk/SM in issue slots (the first version of
-// this kernel used 4 lanes per channel and was issue-bound: profiles/r01_launches_b8_v1.txt).
+// Mapping: LPC lanes per channel (template; 1, 2 or 4), each holding N/LPC states in registers; the lanes of a
+// channel are adjacent, a warp covers 32/LPC consecutive channels, B/C/dt_r are broadcast shared reads.
+// LPC = 1 has no shuffles and no redundant work: per (channel, position) N x (FMUL, MUFU.EX2, FMUL, FFMA, FFMA)
+// + R FFMA (dt_proj) + softplus (measured 150 thread-instr per (channel, position) at N=16, i.e. 4.7 issue
+// clk vs 4.5 MUFU clk per sub-partition) but exposes only batch x K x D/32 warps; LPC = 2 / 4 trade a few
+// shuffles for 2x / 4x the warps when that product cannot fill 148 SMs (profiles/r01_scan_*.txt).
 // CTA = (channel tile DT, direction k [x L-segment], image b) = DT/32 consumer warps + one TMA producer warp.
 // Tiles of LT scan positions are staged HBM -> shared by TMA (cp.async.bulk.tensor) through an NST-deep ring
 // guarded by full/empty mbarriers, so consumer warps never wait for each other (no CTA-wide barrier in the
@@ -47,22 +48,25 @@ __host__ __device__ inline size_t ss2d_smem_bytes(int LT, int DT, int NST, int C
   return NST * stage * sizeof(float) + 128 /*barriers*/;
 }
 
-template <int N, int RP>
+template <int SPT, int RP>
 struct Ss2dThread {
-  float h[N], a2[N], W[RP];
+  float h[SPT], a2[SPT], W[RP];
   float bias, Dv, sumdl;
-  int ch;
+  int ch, q, lane;   // channel within the CTA tile, lane within the channel's group, lane within the warp
   bool ok;
 };
 
-// delta' and u for the 4 positions of group j (tile rows 4j..4j+3)
-template <int N, int RP>
-__device__ __forceinline__ void group_prologue(const Ss2dThread<N, RP> &t, const float *sXC, const float *sDB, int DT,
+// delta' and u for the 4 positions of group j (tile rows 4j..4j+3).  The LPC lanes of a channel split the
+// four dot-product + softplus evaluations between them and exchange the results by shuffle.
+template <int N, int LPC, int RP>
+__device__ __forceinline__ void group_prologue(const Ss2dThread<N / LPC, RP> &t, const float *sXC, const float *sDB, int DT,
                                                int j, float (&dl)[4], float (&u)[4]) {
   constexpr int Cp = 2 * N + RP;  // x_dbl row length: [B | C | dt_r padded to RP] (sigma_ss2d_padded_cp)
+  constexpr int PPL = 4 / LPC;    // positions evaluated by this lane
+  float own[PPL];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float *row = sDB + (4 * j + e) * Cp + 2 * N;
+  for (int e = 0; e < PPL; ++e) {
+    const float *row = sDB + (4 * j + t.q * PPL + e) * Cp + 2 * N;
     float acc = t.bias;
 #pragma unroll
     for (int c = 0; c < RP / 4; ++c) {
@@ -72,26 +76,36 @@ __device__ __forceinline__ void group_prologue(const Ss2dThread<N, RP> &t, const
       acc = fmaf(t.W[4 * c + 2], v.z, acc);
       acc = fmaf(t.W[4 * c + 3], v.w, acc);
     }
-    dl[e] = softplus20(acc);
-    u[e] = sXC[(4 * j + e) * DT + t.ch];
+    own[e] = softplus20(acc);
   }
+  if (LPC == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dl[i] = own[i % PPL];
+  } else {
+    const int base = t.lane & ~(LPC - 1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dl[i] = __shfl_sync(0xffffffffu, own[i % PPL], base + i / PPL);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) u[e] = sXC[(4 * j + e) * DT + t.ch];
 }
 
 // recurrence over `cnt` (<= 4) positions of group j, in walk order (REV: descending tile rows)
-template <int N, int RP, bool WITH_Y, bool REV, bool FULL>
-__device__ __forceinline__ void group_body(Ss2dThread<N, RP> &t, const float *sDB, const float *sDC, float *yrow,
+template <int N, int LPC, int RP, bool WITH_Y, bool REV, bool FULL>
+__device__ __forceinline__ void group_body(Ss2dThread<N / LPC, RP> &t, const float *sDB, const float *sDC, float *yrow,
                                            long long ystride, int j, const float (&dl)[4], const float (&u)[4],
                                            int cnt) {
   constexpr int Cp = 2 * N + RP;
+  constexpr int SPT = N / LPC;
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
     const int i = REV ? 3 - ii : ii;
     if (FULL || i < cnt) {
-      float Bs[N], Cs[N];
-      const float *rb = sDB + (4 * j + i) * Cp;
-      const float *rc = sDC + (4 * j + i) * Cp + N;
+      float Bs[SPT], Cs[SPT];
+      const float *rb = sDB + (4 * j + i) * Cp + t.q * SPT;
+      const float *rc = sDC + (4 * j + i) * Cp + N + t.q * SPT;
 #pragma unroll
-      for (int s4 = 0; s4 < N / 4; ++s4) {
+      for (int s4 = 0; s4 < SPT / 4; ++s4) {
         const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);   // broadcast reads
         Bs[4 * s4] = bv.x; Bs[4 * s4 + 1] = bv.y; Bs[4 * s4 + 2] = bv.z; Bs[4 * s4 + 3] = bv.w;
         if (WITH_Y) {
@@ -102,9 +116,10 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, RP> &t, const float *sD
         }
       }
       float y = 0.f;
-      scan_step<N, WITH_Y>(t.h, t.a2, dl[i], u[i], Bs, Cs, y);
+      scan_step<SPT, WITH_Y>(t.h, t.a2, dl[i], u[i], Bs, Cs, y);
       if (WITH_Y) {
-        if (t.ok) yrow[(long long)(4 * j + i) * ystride] = fmaf(t.Dv, u[i], y);
+        y = channel_reduce<LPC>(y);
+        if (t.ok && t.q == 0) yrow[(long long)(4 * j + i) * ystride] = fmaf(t.Dv, u[i], y);
       } else {
         t.sumdl += dl[i];
       }
@@ -112,38 +127,38 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, RP> &t, const float *sD
   }
 }
 
-template <int N, int RP, bool WITH_Y, bool REV>
-__device__ __forceinline__ void scan_tile(Ss2dThread<N, RP> &t, const float *sXC, const float *sDB, const float *sDC,
+template <int N, int LPC, int RP, bool WITH_Y, bool REV>
+__device__ __forceinline__ void scan_tile(Ss2dThread<N / LPC, RP> &t, const float *sXC, const float *sDB, const float *sDC,
                                           float *yrow, long long ystride, int DT, int npos) {
   const int nfull = npos >> 2, rem = npos & 3;
   float dl[4], u[4];
   if (REV && rem) {  // the ragged group comes first when walking backwards
-    group_prologue<N, RP>(t, sXC, sDB, DT, nfull, dl, u);
-    group_body<N, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
+    group_prologue<N, LPC, RP>(t, sXC, sDB, DT, nfull, dl, u);
+    group_body<N, LPC, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
   }
   if (nfull > 0) {
     int j = REV ? nfull - 1 : 0;
-    group_prologue<N, RP>(t, sXC, sDB, DT, j, dl, u);
+    group_prologue<N, LPC, RP>(t, sXC, sDB, DT, j, dl, u);
 #pragma unroll 1
     for (int g = 0; g < nfull; ++g) {
       // next group's delta'/u first (clamped index: the last iteration recomputes a valid group, unused),
       // so its loads / dot products / softplus overlap this group's exponentials and fma chains
       const int jn = REV ? max(j - 1, 0) : min(j + 1, nfull - 1);
       float dln[4], un[4];
-      group_prologue<N, RP>(t, sXC, sDB, DT, jn, dln, un);
-      group_body<N, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, j, dl, u, 4);
+      group_prologue<N, LPC, RP>(t, sXC, sDB, DT, jn, dln, un);
+      group_body<N, LPC, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, j, dl, u, 4);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { dl[i] = dln[i]; u[i] = un[i]; }
       j = REV ? j - 1 : j + 1;
     }
   }
   if (!REV && rem) {
-    group_prologue<N, RP>(t, sXC, sDB, DT, nfull, dl, u);
-    group_body<N, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
+    group_prologue<N, LPC, RP>(t, sXC, sDB, DT, nfull, dl, u);
+    group_body<N, LPC, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
   }
 }
 
-template <int N, int RP, int MODE>
+template <int N, int LPC, int RP, int MODE>
 __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
@@ -154,18 +169,22 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
   const bool cross = p.kind == SIGMA_DIRS_CROSS;
 
   const int tid = threadIdx.x;
-  const int DT = blockDim.x - 32;            // consumer threads = channels; the last warp is the TMA producer
-  const int nwarps_c = DT >> 5;
-  const bool is_producer = tid >= DT;
+  constexpr int SPT = N / LPC;               // states per thread
+  const int NTC = blockDim.x - 32;           // consumer threads; the last warp is the TMA producer
+  const int DT = NTC / LPC;                  // channels per CTA
+  const int nwarps_c = NTC >> 5;
+  const bool is_producer = tid >= NTC;
   const int xc_fl = LT * DT, dbl_fl = LT * Cp;
   const int stage_fl = xc_fl + dbl_fl * (cross ? 2 : 1);
   uint64_t *full = reinterpret_cast<uint64_t *>(stages + NST * stage_fl);
   uint64_t *empty = full + NST;
 
-  Ss2dThread<N, RP> t;
-  t.ch = tid;
+  Ss2dThread<SPT, RP> t;
+  t.lane = tid & 31;
+  t.q = tid % LPC;
+  t.ch = tid / LPC;
   const int d0 = blockIdx.x * DT;
-  const int d = d0 + tid;
+  const int d = d0 + t.ch;
   t.ok = !is_producer && d < p.D;
   const int k = cross ? 0 : blockIdx.y / p.nsplit;
   const int split = cross ? blockIdx.y : blockIdx.y - k * p.nsplit;
@@ -195,7 +214,7 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
 
   if (is_producer) {
     // ===== TMA producer warp: one elected lane refills a ring slot as soon as every consumer warp released it =====
-    if (tid == DT) {
+    if (tid == NTC) {
       tma_prefetch_desc(&p.m_xc[k]);
       tma_prefetch_desc(&p.m_dbl[k]);
       const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
@@ -217,8 +236,8 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
   // ===== consumer warps: one channel per thread =====
   const long long wd = (long long)kw * p.D + (t.ok ? d : 0);
 #pragma unroll
-  for (int s = 0; s < N; ++s) {
-    t.a2[s] = t.ok ? p.A[wd * N + s] * kLog2e : 0.f;
+  for (int s = 0; s < SPT; ++s) {
+    t.a2[s] = t.ok ? p.A[wd * N + t.q * SPT + s] * kLog2e : 0.f;
     t.h[s] = 0.f;
   }
 #pragma unroll
@@ -231,7 +250,7 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
     carry_row = p.carry + ((((long long)b * p.ndir + k) * p.D + (t.ok ? d : 0)) * p.nsplit + split) * 2 * N;
     if (MODE == MODE_APPLY && t.ok) {
 #pragma unroll
-      for (int s = 0; s < N; ++s) t.h[s] = carry_row[N + s];
+      for (int s = 0; s < SPT; ++s) t.h[s] = carry_row[N + t.q * SPT + s];
     }
   }
   float *ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + (t.ok ? d : 0);
@@ -250,8 +269,8 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
     const int npos = min(LT, I - i0);
     float *yrow = ybase + (long long)o * ostride + (long long)i0 * istride;
 
-    if (rev) scan_tile<N, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
-    else     scan_tile<N, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
+    if (rev) scan_tile<N, LPC, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
+    else     scan_tile<N, LPC, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
 
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[st]);   // this warp is done with ring slot st
@@ -259,15 +278,16 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
 
   if (MODE == MODE_SUMMARY && t.ok) {
 #pragma unroll
-    for (int s = 0; s < N; ++s) {
-      carry_row[s] = ex2(t.a2[s] * t.sumdl);
-      carry_row[N + s] = t.h[s];
+    for (int s = 0; s < SPT; ++s) {
+      carry_row[t.q * SPT + s] = ex2(t.a2[s] * t.sumdl);
+      carry_row[N + t.q * SPT + s] = t.h[s];
     }
   }
 }
 
-// host-side launcher for one (N, RP) instantiation; defined per RP in ss2d_scan_rp*.cu
-template <int N, int RP>
+// host-side launcher for one (N, LPC, RP) instantiation; defined per RP in ss2d_scan_rp*.cu.
+// `nthreads` = consumer threads per CTA (LPC per channel); the launcher adds the producer warp.
+template <int N, int LPC, int RP>
 int ss2d_launch(const Ss2dParams &p, int nthreads, cudaStream_t stream);
 
 }  // namespace sigma
