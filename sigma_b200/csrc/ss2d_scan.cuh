@@ -127,6 +127,53 @@ __device__ __forceinline__ void group_body(Ss2dThread<N / LPC, RP> &t, const flo
   }
 }
 
+// Full group with the exponentials issued ONE POSITION AHEAD of their use: a_cur holds exp2(delta'·A) of the
+// position about to be consumed, and while its fma chains run the SPT MUFU.EX2 of the following position are
+// already in flight.  An in-order warp then never waits on a MUFU it has just issued (a single warp per
+// sub-partition with 16 independent ex2 in flight reaches 15/16 of the MUFU peak: scripts/mufu_bench.cu).
+template <int N, int LPC, int RP, bool WITH_Y, bool REV>
+__device__ __forceinline__ void group_body_pipe(Ss2dThread<N / LPC, RP> &t, const float *sDB, const float *sDC, float *yrow,
+                                                long long ystride, int j, const float (&dl)[4], const float (&u)[4],
+                                                float dl_after, float (&a_cur)[N / LPC]) {
+  constexpr int Cp = 2 * N + RP;
+  constexpr int SPT = N / LPC;
+#pragma unroll
+  for (int ii = 0; ii < 4; ++ii) {
+    const int i = REV ? 3 - ii : ii;
+    const float dn = ii < 3 ? dl[REV ? i - 1 : i + 1] : dl_after;
+    float a_nxt[SPT];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) a_nxt[s] = ex2(dn * t.a2[s]);
+    const float *rb = sDB + (4 * j + i) * Cp + t.q * SPT;
+    const float *rc = sDC + (4 * j + i) * Cp + N + t.q * SPT;
+    const float dlu = dl[i] * u[i];
+    float y = 0.f;
+#pragma unroll
+    for (int s4 = 0; s4 < SPT / 4; ++s4) {
+      const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);
+      t.h[4 * s4 + 0] = fmaf(a_cur[4 * s4 + 0], t.h[4 * s4 + 0], dlu * bv.x);
+      t.h[4 * s4 + 1] = fmaf(a_cur[4 * s4 + 1], t.h[4 * s4 + 1], dlu * bv.y);
+      t.h[4 * s4 + 2] = fmaf(a_cur[4 * s4 + 2], t.h[4 * s4 + 2], dlu * bv.z);
+      t.h[4 * s4 + 3] = fmaf(a_cur[4 * s4 + 3], t.h[4 * s4 + 3], dlu * bv.w);
+      if (WITH_Y) {
+        const float4 cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
+        y = fmaf(t.h[4 * s4 + 0], cv.x, y);
+        y = fmaf(t.h[4 * s4 + 1], cv.y, y);
+        y = fmaf(t.h[4 * s4 + 2], cv.z, y);
+        y = fmaf(t.h[4 * s4 + 3], cv.w, y);
+      }
+    }
+    if (WITH_Y) {
+      y = channel_reduce<LPC>(y);
+      if (t.ok && t.q == 0) yrow[(long long)(4 * j + i) * ystride] = fmaf(t.Dv, u[i], y);
+    } else {
+      t.sumdl += dl[i];
+    }
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) a_cur[s] = a_nxt[s];
+  }
+}
+
 template <int N, int LPC, int RP, bool WITH_Y, bool REV>
 __device__ __forceinline__ void scan_tile(Ss2dThread<N / LPC, RP> &t, const float *sXC, const float *sDB, const float *sDC,
                                           float *yrow, long long ystride, int DT, int npos) {
@@ -139,6 +186,9 @@ __device__ __forceinline__ void scan_tile(Ss2dThread<N / LPC, RP> &t, const floa
   if (nfull > 0) {
     int j = REV ? nfull - 1 : 0;
     group_prologue<N, LPC, RP>(t, sXC, sDB, DT, j, dl, u);
+    float a_cur[N / LPC];
+#pragma unroll
+    for (int s = 0; s < N / LPC; ++s) a_cur[s] = ex2(dl[REV ? 3 : 0] * t.a2[s]);
 #pragma unroll 1
     for (int g = 0; g < nfull; ++g) {
       // next group's delta'/u first (clamped index: the last iteration recomputes a valid group, unused),
@@ -146,7 +196,7 @@ __device__ __forceinline__ void scan_tile(Ss2dThread<N / LPC, RP> &t, const floa
       const int jn = REV ? max(j - 1, 0) : min(j + 1, nfull - 1);
       float dln[4], un[4];
       group_prologue<N, LPC, RP>(t, sXC, sDB, DT, jn, dln, un);
-      group_body<N, LPC, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, j, dl, u, 4);
+      group_body_pipe<N, LPC, RP, WITH_Y, REV>(t, sDB, sDC, yrow, ystride, j, dl, u, dln[REV ? 3 : 0], a_cur);
 #pragma unroll
       for (int i = 0; i < 4; ++i) { dl[i] = dln[i]; u[i] = un[i]; }
       j = REV ? j - 1 : j + 1;
