@@ -67,16 +67,16 @@ __device__ __forceinline__ void group_prologue(const Ss2dThread<N / LPC, RP> &t,
 #pragma unroll
   for (int e = 0; e < PPL; ++e) {
     const float *row = sDB + (4 * j + t.q * PPL + e) * Cp + 2 * N;
-    float acc = t.bias;
+    float acc0 = t.bias, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // 4 accumulators: short dependency chains
 #pragma unroll
     for (int c = 0; c < RP / 4; ++c) {
       const float4 v = *reinterpret_cast<const float4 *>(row + 4 * c);   // broadcast read
-      acc = fmaf(t.W[4 * c + 0], v.x, acc);
-      acc = fmaf(t.W[4 * c + 1], v.y, acc);
-      acc = fmaf(t.W[4 * c + 2], v.z, acc);
-      acc = fmaf(t.W[4 * c + 3], v.w, acc);
+      acc0 = fmaf(t.W[4 * c + 0], v.x, acc0);
+      acc1 = fmaf(t.W[4 * c + 1], v.y, acc1);
+      acc2 = fmaf(t.W[4 * c + 2], v.z, acc2);
+      acc3 = fmaf(t.W[4 * c + 3], v.w, acc3);
     }
-    own[e] = softplus20(acc);
+    own[e] = softplus20((acc0 + acc1) + (acc2 + acc3));
   }
   if (LPC == 1) {
 #pragma unroll
@@ -147,7 +147,8 @@ __device__ __forceinline__ void group_body_pipe(Ss2dThread<N / LPC, RP> &t, cons
     const float *rb = sDB + (4 * j + i) * Cp + t.q * SPT;
     const float *rc = sDC + (4 * j + i) * Cp + N + t.q * SPT;
     const float dlu = dl[i] * u[i];
-    float y = 0.f;
+    // all state updates first (SPT independent fma), then the C·h dot product on 4 accumulators: no fma waits
+    // on a result produced less than ~4 instructions earlier (an in-order warp stalls on every such pair)
 #pragma unroll
     for (int s4 = 0; s4 < SPT / 4; ++s4) {
       const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);
@@ -155,13 +156,19 @@ __device__ __forceinline__ void group_body_pipe(Ss2dThread<N / LPC, RP> &t, cons
       t.h[4 * s4 + 1] = fmaf(a_cur[4 * s4 + 1], t.h[4 * s4 + 1], dlu * bv.y);
       t.h[4 * s4 + 2] = fmaf(a_cur[4 * s4 + 2], t.h[4 * s4 + 2], dlu * bv.z);
       t.h[4 * s4 + 3] = fmaf(a_cur[4 * s4 + 3], t.h[4 * s4 + 3], dlu * bv.w);
-      if (WITH_Y) {
+    }
+    float y = 0.f;
+    if (WITH_Y) {
+      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
+#pragma unroll
+      for (int s4 = 0; s4 < SPT / 4; ++s4) {
         const float4 cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
-        y = fmaf(t.h[4 * s4 + 0], cv.x, y);
-        y = fmaf(t.h[4 * s4 + 1], cv.y, y);
-        y = fmaf(t.h[4 * s4 + 2], cv.z, y);
-        y = fmaf(t.h[4 * s4 + 3], cv.w, y);
+        y0 = fmaf(t.h[4 * s4 + 0], cv.x, y0);
+        y1 = fmaf(t.h[4 * s4 + 1], cv.y, y1);
+        y2 = fmaf(t.h[4 * s4 + 2], cv.z, y2);
+        y3 = fmaf(t.h[4 * s4 + 3], cv.w, y3);
       }
+      y = (y0 + y1) + (y2 + y3);
     }
     if (WITH_Y) {
       y = channel_reduce<LPC>(y);
