@@ -113,7 +113,7 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
     const int v = atoi(e);
     if ((v == 1 || v == 2 || v == 4) && N % (4 * v) == 0) lpc = v;
   }
-  int maxw = 8;
+  int maxw = 4;  // 4 consumer warps + 1 producer per CTA measured best on B200 (profiles/r01_scan_variants.txt)
   if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(8, atoi(e)));
   const int NW = pick_warps(D, lpc, maxw), DT = (32 / lpc) * NW;
   int rc;
