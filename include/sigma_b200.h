@@ -72,6 +72,25 @@ int sigma_scan_fwd(const void *u, const void *delta, const float *A, const void 
                    void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * a3. backward of a1.
+ * Replaces `selective_scan_cuda_core.bwd(u, delta, A, B, C, D, delta_bias, dout, x,
+ * delta_softplus, nrows) -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]`
+ * (selective_scan.cpp:251-362, selective_scan_bwd_kernel.cuh:68-274).
+ * All tensors contiguous (d_state <= 16).  `workspace` holds the per-tile forward states of the recompute sweep;
+ * the reference's `x` is not needed.  du, ddelta: (batch, dim, seqlen) in `dtype`; dA (dim, dstate),
+ * dD, ddelta_bias (dim) fp32 — OVERWRITTEN (not accumulated); dB, dC (batch, ngroups, dstate,
+ * seqlen) fp32, overwritten.  dD / ddelta_bias may be NULL when D / delta_bias are NULL.
+ * ------------------------------------------------------------------------------------------ */
+size_t sigma_scan_bwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype);
+
+int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void *B, const void *C,
+                   const float *D, const float *delta_bias, const void *dout,
+                   void *du, void *ddelta, float *dA, float *dB, float *dC, float *dD,
+                   float *ddelta_bias,
+                   int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
+                   int delta_softplus, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * a4+a5 (+a8/a9 cores). Fused multi-direction SS2D scan, channels-last.
  * Replaces, in one launch, CrossScan (vmamba.py:80-98) + the dt_proj einsum (vmamba.py:199) +
  * delta_bias/softplus + SelectiveScan (vmamba.py:213) + the un-flip / un-transpose half of

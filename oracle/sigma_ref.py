@@ -262,3 +262,24 @@ def mean_iou(pred, gt, n_cl):
     hist = np.bincount(n_cl * gt[k].astype(int) + pred[k].astype(int), minlength=n_cl ** 2).reshape(n_cl, n_cl)
     iou = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
     return iou, float(np.nanmean(iou))
+
+
+def selective_scan_torch(u, delta, A, B, C, D=None, delta_bias=None, delta_softplus=False):
+    """Differentiable pure-torch restatement of selective_scan_ref (selective_scan_interface.py:86-131), used to
+    check the TRAINING path (autograd through sigma_b200.ops.SelectiveScan) on small shapes.  B, C: (b, G, N, L)."""
+    b, d, L = u.shape
+    G, N = B.shape[1], B.shape[2]
+    delta = delta + (delta_bias[None, :, None] if delta_bias is not None else 0.0)
+    if delta_softplus:
+        delta = F.softplus(delta)
+    Bx = B.repeat_interleave(d // G, dim=1)          # (b, d, N, L)
+    Cx = C.repeat_interleave(d // G, dim=1)
+    dA = torch.exp(delta[:, :, None, :] * A[None, :, :, None])
+    dBu = (delta * u)[:, :, None, :] * Bx
+    h = u.new_zeros((b, d, N))
+    ys = []
+    for l in range(L):
+        h = dA[..., l] * h + dBu[..., l]
+        ys.append((h * Cx[..., l]).sum(-1))
+    y = torch.stack(ys, dim=-1)
+    return y if D is None else y + u * D[None, :, None]

@@ -29,6 +29,13 @@ int scan_op_fwd_f32(const float *u, const float *delta, const float *A, const fl
                     int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
                     int force_split, cudaStream_t stream);
 
+// implemented in scan_op_bwd.cu
+size_t scan_op_bwd_workspace_bytes(int batch, int dim, int L, int N);
+int scan_op_bwd_f32(const float *u, const float *delta, const float *A, const float *B, const float *C, const float *D,
+                    const float *bias, const float *dout, float *du, float *ddelta, float *dA, float *dB, float *dC,
+                    float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
+                    size_t ws_bytes, cudaStream_t stream);
+
 // ---- half <-> float staging for the op-level boundary (u, delta, B, C, out may be fp16/bf16,
 // selective_scan.cpp:175-180; all arithmetic is fp32 either way) ----
 template <typename T>
@@ -323,6 +330,65 @@ int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const f
   SIGMA_CHECK_ARG(rows >= 0 && rows_per_batch > 0 && C > 0 && C % 4 == 0 && al16(a) && al16(sa) && al16(b) && al16(sb) && al16(out),
                   "sigma_scale_add_fwd: bad sizes / alignment");
   return scale_add_launch(a, sa, b, sb, out, rows, rows_per_batch, C, (cudaStream_t)stream);
+}
+
+size_t sigma_scan_bwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype) {
+  size_t w = align256(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate));
+  if (dtype != SIGMA_F32) {
+    const size_t bdl = align256((size_t)batch * dim * seqlen * sizeof(float));
+    const size_t bgnl = align256((size_t)batch * ngroups * dstate * seqlen * sizeof(float));
+    w += 5 * bdl + 2 * bgnl;   // u, delta, dout, du, ddelta + B, C
+  }
+  return w;
+}
+
+int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                   const float *delta_bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                   float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
+                   int delta_softplus, void *workspace, size_t workspace_bytes, void *stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SIGMA_CHECK_ARG(u && delta && A && B && C && dout && du && ddelta && dA && dB && dC, "sigma_scan_bwd: null pointer argument");
+  SIGMA_CHECK_ARG((D == nullptr || dD != nullptr) && (delta_bias == nullptr || ddelta_bias != nullptr),
+                  "sigma_scan_bwd: dD / ddelta_bias required when D / delta_bias are given");
+  SIGMA_CHECK_ARG(batch > 0 && dim > 0 && seqlen > 0 && dstate > 0 && ngroups > 0 && dim % ngroups == 0,
+                  "sigma_scan_bwd: bad sizes (batch=%d dim=%d seqlen=%d dstate=%d ngroups=%d)", batch, dim, seqlen, dstate, ngroups);
+  SIGMA_CHECK_ARG(dtype == SIGMA_F32 || dtype == SIGMA_F16 || dtype == SIGMA_BF16, "sigma_scan_bwd: unknown dtype %d", dtype);
+  const size_t need = sigma_scan_bwd_workspace_bytes(batch, dim, seqlen, dstate, ngroups, dtype);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("sigma_scan_bwd: needs %zu workspace bytes, got %zu", need, workspace_bytes);
+    return SIGMA_EWORKSPACE;
+  }
+  const size_t core_b = align256(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate));
+  if (dtype == SIGMA_F32)
+    return scan_op_bwd_f32((const float *)u, (const float *)delta, A, (const float *)B, (const float *)C, D, delta_bias,
+                           (const float *)dout, (float *)du, (float *)ddelta, dA, dB, dC, dD, ddelta_bias, batch, dim, seqlen,
+                           dstate, ngroups, delta_softplus, workspace, core_b, stream);
+  char *w = (char *)workspace + core_b;
+  const size_t bdl = align256((size_t)batch * dim * seqlen * sizeof(float));
+  const size_t bgnl = align256((size_t)batch * ngroups * dstate * seqlen * sizeof(float));
+  float *u32 = (float *)w, *d32 = (float *)(w + bdl), *o32 = (float *)(w + 2 * bdl), *du32 = (float *)(w + 3 * bdl),
+        *dd32 = (float *)(w + 4 * bdl), *B32 = (float *)(w + 5 * bdl), *C32 = (float *)(w + 5 * bdl + bgnl);
+  const long long sb = (long long)dim * seqlen, sg = (long long)dstate * seqlen, sbb = (long long)ngroups * sg;
+  int rc;
+#define CAST_ALL(T)                                                                                   \
+  do {                                                                                                \
+    if ((rc = cast_in<T>(u, u32, batch, dim, 1, seqlen, sb, seqlen, 0, stream))) return rc;            \
+    if ((rc = cast_in<T>(delta, d32, batch, dim, 1, seqlen, sb, seqlen, 0, stream))) return rc;        \
+    if ((rc = cast_in<T>(dout, o32, batch, dim, 1, seqlen, sb, seqlen, 0, stream))) return rc;         \
+    if ((rc = cast_in<T>(B, B32, batch, ngroups, dstate, seqlen, sbb, sg, seqlen, stream))) return rc; \
+    if ((rc = cast_in<T>(C, C32, batch, ngroups, dstate, seqlen, sbb, sg, seqlen, stream))) return rc; \
+  } while (0)
+  if (dtype == SIGMA_F16) CAST_ALL(__half); else CAST_ALL(__nv_bfloat16);
+#undef CAST_ALL
+  rc = scan_op_bwd_f32(u32, d32, A, B32, C32, D, delta_bias, o32, du32, dd32, dA, dB, dC, dD, ddelta_bias, batch, dim, seqlen,
+                       dstate, ngroups, delta_softplus, workspace, core_b, stream);
+  if (rc) return rc;
+  if (dtype == SIGMA_F16) {
+    if ((rc = cast_out<__half>(du32, du, batch, dim, seqlen, sb, seqlen, stream))) return rc;
+    return cast_out<__half>(dd32, ddelta, batch, dim, seqlen, sb, seqlen, stream);
+  }
+  if ((rc = cast_out<__nv_bfloat16>(du32, du, batch, dim, seqlen, sb, seqlen, stream))) return rc;
+  return cast_out<__nv_bfloat16>(dd32, ddelta, batch, dim, seqlen, sb, seqlen, stream);
 }
 
 #pragma GCC visibility pop

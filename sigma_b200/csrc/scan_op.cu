@@ -23,6 +23,7 @@ constexpr int OP_NST = 2;   // cp.async stages
 struct ScanOpParams {
   const float *u, *delta, *A, *B, *C, *D, *bias;
   float *out, *x, *carry;
+  float *hs;  // optional: state at the START of every 32-position tile, (batch, dim, ntiles, NP) — consumed by the backward
   int batch, dim, L, N, G, dpg, tiles_per_group;
   int softplus;
   long long u_b, u_d, dl_b, dl_d, A_d, A_n, B_b, B_g, B_n, C_b, C_g, C_n, o_b, o_d;
@@ -130,6 +131,11 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
     cp_async_wait<1>();
     __syncthreads();
 
+    if (MODE == MODE_SERIAL && p.hs != nullptr && ch_ok) {
+      float *hrow = p.hs + (((long long)b * p.dim + d) * p.ntiles + t) * NP + q * SPT;
+#pragma unroll
+      for (int s = 0; s < SPT; ++s) hrow[s] = h[s];
+    }
     const float *sU = smem + st * STAGE_ROWS * OP_LTP;
     const float *sDl = sU + OP_DT * OP_LTP;
     const float *sB = sDl + OP_DT * OP_LTP;
@@ -319,11 +325,28 @@ size_t scan_op_workspace_bytes(int batch, int dim, int dstate) {
   return (size_t)batch * dim * 64 * 2 * pick_npad(dstate) * sizeof(float);
 }
 
+int scan_op_fwd_f32_hs(const float *u, const float *delta, const float *A, const float *B, const float *C,
+                       const float *D, const float *bias, float *out, float *x, float *hs, int batch, int dim, int L,
+                       int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
+                       int force_split, cudaStream_t stream);
+
 int scan_op_fwd_f32(const float *u, const float *delta, const float *A, const float *B, const float *C,
                     const float *D, const float *bias, float *out, float *x, int batch, int dim, int L,
                     int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
                     int force_split, cudaStream_t stream) {
+  return scan_op_fwd_f32_hs(u, delta, A, B, C, D, bias, out, x, nullptr, batch, dim, L, N, G, softplus, s, ws, ws_bytes,
+                            force_split, stream);
+}
+
+int scan_op_npad(int N) { return pick_npad(N); }
+
+int scan_op_fwd_f32_hs(const float *u, const float *delta, const float *A, const float *B, const float *C,
+                       const float *D, const float *bias, float *out, float *x, float *hs, int batch, int dim, int L,
+                       int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
+                       int force_split, cudaStream_t stream) {
   ScanOpParams p;
+  p.hs = hs;
+  if (hs != nullptr) force_split = 1;  // checkpoints are written by the serial walk only
   p.u = u; p.delta = delta; p.A = A; p.B = B; p.C = C; p.D = D; p.bias = bias;
   p.out = out; p.x = x; p.carry = (float *)ws;
   p.batch = batch; p.dim = dim; p.L = L; p.N = N; p.G = G; p.dpg = dim / G;
