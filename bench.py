@@ -223,13 +223,11 @@ def main():
         return run_reference(a)
 
     import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from sigma_b200 import dist_util
+    world, rank, local = dist_util.env_world()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dist_util.init("nccl", dev)
 
     from sigma_b200 import _lib, modules as M
     # dense projections run on the tensor cores in TF32 (fp32 storage, fp32 accumulate); the scan is fp32
@@ -241,7 +239,7 @@ def main():
     with contextlib.redirect_stdout(io.StringIO()):
         model = M.EncoderDecoder(cfg_of(a), criterion=None).to(dev).eval()
     B = a.batch
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    g = torch.Generator(device=dev).manual_seed(dist_util.shard_seed(1234, rank))
     rgb = torch.randn(B, 3, a.height, a.width, device=dev, generator=g)
     mx = torch.randn(B, 3, a.height, a.width, device=dev, generator=g)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -301,10 +299,7 @@ def main():
         e1.record()
     barrier()
     total_ms = sum(e0.elapsed_time(e1) for e0, e1 in ev)
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = dist_util.max_over_ranks(total_ms, dev)
 
     # ---- timed region 2: end to end through the public call, host buffers
     h_rgb = torch.randn(B, 3, a.height, a.width).pin_memory()
@@ -324,10 +319,7 @@ def main():
         e2e_step()
     s1.record()
     barrier()
-    t2 = torch.tensor([s0.elapsed_time(s1)], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t2.item())
+    e2e_ms = dist_util.max_over_ranks(s0.elapsed_time(s1), dev)
     clocks = sampler.stop() if sampler else None
 
     if rank != 0:
@@ -369,8 +361,8 @@ def main():
     in_bytes = 2 * B * 3 * a.height * a.width * 4
     out_bytes = static_out.numel() * static_out.element_size()
     line = {
-        "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(n_img / (total_ms * 1e-3), 3), "unit": "images/s",
-        "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(total_ms / a.steps, 4),
+        "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(dist_util.aggregate_images_per_s(B, world, a.steps, total_ms), 3),
+        "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(total_ms / a.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"replicas x{world} (no data-path collective)", "scan_math": "fp32",
