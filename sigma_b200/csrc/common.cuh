@@ -79,6 +79,30 @@ __device__ __forceinline__ float softplus20(float x) {
   return fmaxf(x, 0.f) + (z < 0.015625f ? poly : lg);
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2: two fp32 lanes per instruction, same FLOP rate as the
+// scalar pipe but half the issue slots — scripts/mufu_bench.cu).  Operands are adjacent register pairs.
+struct f2 { float x, y; };
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f2 unpack2(unsigned long long r) {
+  f2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  unsigned long long rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)), "l"(pack2(c.x, c.y)));
+  return unpack2(rd);
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  unsigned long long rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(pack2(a.x, a.y)), "l"(pack2(b.x, b.y)));
+  return unpack2(rd);
+}
+
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.f + ex2(-x * kLog2e)); }
 
 // ---- cp.async (LDGSTS) ----

@@ -7,12 +7,14 @@
 //   softplus -> selective scan (state in registers, one MUFU.EX2 per element) -> D skip -> store at the
 //   POSITION the value belongs to (so CrossMerge's un-flip / un-transpose disappear).
 //
-// Mapping: LPC lanes per channel (template; 1, 2 or 4), each holding N/LPC states in registers; the lanes of a
-// channel are adjacent, a warp covers 32/LPC consecutive channels, B/C/dt_r are broadcast shared reads.
-// LPC = 1 has no shuffles and no redundant work: per (channel, position) N x (FMUL, MUFU.EX2, FMUL, FFMA, FFMA)
-// + R FFMA (dt_proj) + softplus (measured 150 thread-instr per (channel, position) at N=16, i.e. 4.7 issue
-// clk vs 4.5 MUFU clk per sub-partition) but exposes only batch x K x D/32 warps; LPC = 2 / 4 trade a few
-// shuffles for 2x / 4x the warps when that product cannot fill 148 SMs (profiles/r01_scan_*.txt).
+// Mapping: one thread owns CPT (1 or 2) channels with all N states of each in registers; a warp covers 32
+// consecutive channels (and the 32 that lie DT/2 further for CPT = 2), so every global / shared access of a warp
+// is a 128-byte row and B / C / dt_r are broadcast shared reads shared by the thread's channels.  No shuffles.
+// The recurrence runs on packed fp32x2 instructions (FFMA2 / FMUL2 over state pairs): per (channel, position)
+// and state pair FMUL2 + 2 MUFU.EX2 + FMUL2 + FFMA2 + FFMA2, i.e. 3 issue slots per element instead of 5.
+// History (profiles/r01_scan_variants.txt): 4 lanes/channel was issue-bound; 1 thread/channel with scalar
+// fp32 left MUFU, the LDS return path (2N floats of B/C per channel-position) and issue each ~50 % busy;
+// CPT = 2 halves the B/C traffic per channel and FFMA2 halves the fp32 issue slots.
 // CTA = (channel tile DT, direction k [x L-segment], image b) = DT/32 consumer warps + one TMA producer warp.
 // Tiles of LT scan positions are staged HBM -> shared by TMA (cp.async.bulk.tensor) through an NST-deep ring
 // guarded by full/empty mbarriers, so consumer warps never wait for each other (no CTA-wide barrier in the
@@ -48,175 +50,130 @@ __host__ __device__ inline size_t ss2d_smem_bytes(int LT, int DT, int NST, int C
   return NST * stage * sizeof(float) + 128 /*barriers*/;
 }
 
-template <int SPT, int RP>
+template <int N, int CPT, int RP>
 struct Ss2dThread {
-  float h[SPT], a2[SPT], W[RP];
-  float bias, Dv, sumdl;
-  int ch, q, lane;   // channel within the CTA tile, lane within the channel's group, lane within the warp
-  bool ok;
+  float h[CPT][N], a2[CPT][N], W[CPT][RP];
+  float bias[CPT], Dv[CPT], sumdl[CPT];
+  int ch;          // first channel of this thread inside the CTA tile; the c-th is ch + c*DT/CPT
+  bool ok[CPT];
 };
 
-// delta' and u for the 4 positions of group j (tile rows 4j..4j+3).  The LPC lanes of a channel split the
-// four dot-product + softplus evaluations between them and exchange the results by shuffle.
-template <int N, int LPC, int RP>
-__device__ __forceinline__ void group_prologue(const Ss2dThread<N / LPC, RP> &t, const float *sXC, const float *sDB, int DT,
-                                               int j, float (&dl)[4], float (&u)[4]) {
+// delta' and u of both channels for the 4 positions of group j (tile rows 4j..4j+3).  dt_r is read once per
+// position (broadcast LDS.128) and used for all CPT channels; the dot products run on FFMA2 pairs.
+template <int N, int CPT, int RP>
+__device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, const float *sXC, const float *sDB, int DT,
+                                               int j, float (&dl)[CPT][4], float (&u)[CPT][4]) {
   constexpr int Cp = 2 * N + RP;  // x_dbl row length: [B | C | dt_r padded to RP] (sigma_ss2d_padded_cp)
-  constexpr int PPL = 4 / LPC;    // positions evaluated by this lane
-  float own[PPL];
+  const int cstride = DT / CPT;
 #pragma unroll
-  for (int e = 0; e < PPL; ++e) {
-    const float *row = sDB + (4 * j + t.q * PPL + e) * Cp + 2 * N;
-    float acc0 = t.bias, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // 4 accumulators: short dependency chains
+  for (int e = 0; e < 4; ++e) {
+    const float *row = sDB + (4 * j + e) * Cp + 2 * N;
+    f2 acc[CPT][2];
 #pragma unroll
-    for (int c = 0; c < RP / 4; ++c) {
-      const float4 v = *reinterpret_cast<const float4 *>(row + 4 * c);   // broadcast read
-      acc0 = fmaf(t.W[4 * c + 0], v.x, acc0);
-      acc1 = fmaf(t.W[4 * c + 1], v.y, acc1);
-      acc2 = fmaf(t.W[4 * c + 2], v.z, acc2);
-      acc3 = fmaf(t.W[4 * c + 3], v.w, acc3);
+    for (int c = 0; c < CPT; ++c) { acc[c][0] = f2{t.bias[c], 0.f}; acc[c][1] = f2{0.f, 0.f}; }
+#pragma unroll
+    for (int q4 = 0; q4 < RP / 4; ++q4) {
+      const float4 v = *reinterpret_cast<const float4 *>(row + 4 * q4);   // broadcast read, shared by CPT channels
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        acc[c][0] = fma2(f2{t.W[c][4 * q4 + 0], t.W[c][4 * q4 + 1]}, f2{v.x, v.y}, acc[c][0]);
+        acc[c][1] = fma2(f2{t.W[c][4 * q4 + 2], t.W[c][4 * q4 + 3]}, f2{v.z, v.w}, acc[c][1]);
+      }
     }
-    own[e] = softplus20((acc0 + acc1) + (acc2 + acc3));
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      dl[c][e] = softplus20((acc[c][0].x + acc[c][0].y) + (acc[c][1].x + acc[c][1].y));
+      u[c][e] = sXC[(4 * j + e) * DT + t.ch + c * cstride];
+    }
   }
-  if (LPC == 1) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dl[i] = own[i % PPL];
-  } else {
-    const int base = t.lane & ~(LPC - 1);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dl[i] = __shfl_sync(0xffffffffu, own[i % PPL], base + i / PPL);
-  }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) u[e] = sXC[(4 * j + e) * DT + t.ch];
 }
 
-// recurrence over `cnt` (<= 4) positions of group j, in walk order (REV: descending tile rows)
-template <int N, int LPC, int RP, bool WITH_Y, bool REV, bool FULL>
-__device__ __forceinline__ void group_body(Ss2dThread<N / LPC, RP> &t, const float *sDB, const float *sDC, float *yrow,
-                                           long long ystride, int j, const float (&dl)[4], const float (&u)[4],
-                                           int cnt) {
+// recurrence over `cnt` (<= 4) positions of group j, in walk order (REV: descending tile rows).
+// Per position B and C are read ONCE (2·N/4 broadcast LDS.128) and reused by the CPT channels of the thread;
+// per channel and state pair: FMUL2 (exp arguments), 2 x MUFU.EX2, FMUL2 (delta·u·B), FFMA2 (h), FFMA2 (C·h).
+template <int N, int CPT, int RP, bool WITH_Y, bool REV, bool FULL>
+__device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *sDB, const float *sDC, float *yrow,
+                                           long long ystride, int ycstride, int j, const float (&dl)[CPT][4],
+                                           const float (&u)[CPT][4], int cnt) {
   constexpr int Cp = 2 * N + RP;
-  constexpr int SPT = N / LPC;
 #pragma unroll
   for (int ii = 0; ii < 4; ++ii) {
     const int i = REV ? 3 - ii : ii;
     if (FULL || i < cnt) {
-      float Bs[SPT], Cs[SPT];
-      const float *rb = sDB + (4 * j + i) * Cp + t.q * SPT;
-      const float *rc = sDC + (4 * j + i) * Cp + N + t.q * SPT;
+      const float *rb = sDB + (4 * j + i) * Cp;
+      const float *rc = sDC + (4 * j + i) * Cp + N;
+      f2 yacc[CPT][2];
 #pragma unroll
-      for (int s4 = 0; s4 < SPT / 4; ++s4) {
+      for (int c = 0; c < CPT; ++c) yacc[c][0] = yacc[c][1] = f2{0.f, 0.f};
+#pragma unroll
+      for (int s4 = 0; s4 < N / 4; ++s4) {
         const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);   // broadcast reads
-        Bs[4 * s4] = bv.x; Bs[4 * s4 + 1] = bv.y; Bs[4 * s4 + 2] = bv.z; Bs[4 * s4 + 3] = bv.w;
-        if (WITH_Y) {
-          const float4 cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
-          Cs[4 * s4] = cv.x; Cs[4 * s4 + 1] = cv.y; Cs[4 * s4 + 2] = cv.z; Cs[4 * s4 + 3] = cv.w;
-        } else {
-          Cs[4 * s4] = Cs[4 * s4 + 1] = Cs[4 * s4 + 2] = Cs[4 * s4 + 3] = 0.f;
+        float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (WITH_Y) cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const float d = dl[c][i], du = dl[c][i] * u[c][i];
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {                                   // state pair (4·s4 + 2·hp, +1)
+            const int s = 4 * s4 + 2 * hp;
+            const f2 arg = mul2(f2{d, d}, f2{t.a2[c][s], t.a2[c][s + 1]});
+            const f2 a = f2{ex2(arg.x), ex2(arg.y)};
+            const f2 bb = mul2(f2{du, du}, hp == 0 ? f2{bv.x, bv.y} : f2{bv.z, bv.w});
+            const f2 hn = fma2(a, f2{t.h[c][s], t.h[c][s + 1]}, bb);
+            t.h[c][s] = hn.x; t.h[c][s + 1] = hn.y;
+            if (WITH_Y) yacc[c][hp] = fma2(hn, hp == 0 ? f2{cv.x, cv.y} : f2{cv.z, cv.w}, yacc[c][hp]);
+          }
         }
       }
-      float y = 0.f;
-      scan_step<SPT, WITH_Y>(t.h, t.a2, dl[i], u[i], Bs, Cs, y);
-      if (WITH_Y) {
-        y = channel_reduce<LPC>(y);
-        if (t.ok && t.q == 0) yrow[(long long)(4 * j + i) * ystride] = fmaf(t.Dv, u[i], y);
-      } else {
-        t.sumdl += dl[i];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        if (WITH_Y) {
+          const float y = (yacc[c][0].x + yacc[c][0].y) + (yacc[c][1].x + yacc[c][1].y);
+          if (t.ok[c]) yrow[(long long)(4 * j + i) * ystride + c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
+        } else {
+          t.sumdl[c] += dl[c][i];
+        }
       }
     }
   }
 }
 
-// Full group with the exponentials issued ONE POSITION AHEAD of their use: a_cur holds exp2(delta'·A) of the
-// position about to be consumed, and while its fma chains run the SPT MUFU.EX2 of the following position are
-// already in flight.  An in-order warp then never waits on a MUFU it has just issued (a single warp per
-// sub-partition with 16 independent ex2 in flight reaches 15/16 of the MUFU peak: scripts/mufu_bench.cu).
-template <int N, int LPC, int RP, bool WITH_Y, bool REV>
-__device__ __forceinline__ void group_body_pipe(Ss2dThread<N / LPC, RP> &t, const float *sDB, const float *sDC, float *yrow,
-                                                long long ystride, int j, const float (&dl)[4], const float (&u)[4],
-                                                float dl_after, float (&a_cur)[N / LPC]) {
-  constexpr int Cp = 2 * N + RP;
-  constexpr int SPT = N / LPC;
-#pragma unroll
-  for (int ii = 0; ii < 4; ++ii) {
-    const int i = REV ? 3 - ii : ii;
-    const float dn = ii < 3 ? dl[REV ? i - 1 : i + 1] : dl_after;
-    float a_nxt[SPT];
-#pragma unroll
-    for (int s = 0; s < SPT; ++s) a_nxt[s] = ex2(dn * t.a2[s]);
-    const float *rb = sDB + (4 * j + i) * Cp + t.q * SPT;
-    const float *rc = sDC + (4 * j + i) * Cp + N + t.q * SPT;
-    const float dlu = dl[i] * u[i];
-    // all state updates first (SPT independent fma), then the C·h dot product on 4 accumulators: no fma waits
-    // on a result produced less than ~4 instructions earlier (an in-order warp stalls on every such pair)
-#pragma unroll
-    for (int s4 = 0; s4 < SPT / 4; ++s4) {
-      const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);
-      t.h[4 * s4 + 0] = fmaf(a_cur[4 * s4 + 0], t.h[4 * s4 + 0], dlu * bv.x);
-      t.h[4 * s4 + 1] = fmaf(a_cur[4 * s4 + 1], t.h[4 * s4 + 1], dlu * bv.y);
-      t.h[4 * s4 + 2] = fmaf(a_cur[4 * s4 + 2], t.h[4 * s4 + 2], dlu * bv.z);
-      t.h[4 * s4 + 3] = fmaf(a_cur[4 * s4 + 3], t.h[4 * s4 + 3], dlu * bv.w);
-    }
-    float y = 0.f;
-    if (WITH_Y) {
-      float y0 = 0.f, y1 = 0.f, y2 = 0.f, y3 = 0.f;
-#pragma unroll
-      for (int s4 = 0; s4 < SPT / 4; ++s4) {
-        const float4 cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
-        y0 = fmaf(t.h[4 * s4 + 0], cv.x, y0);
-        y1 = fmaf(t.h[4 * s4 + 1], cv.y, y1);
-        y2 = fmaf(t.h[4 * s4 + 2], cv.z, y2);
-        y3 = fmaf(t.h[4 * s4 + 3], cv.w, y3);
-      }
-      y = (y0 + y1) + (y2 + y3);
-    }
-    if (WITH_Y) {
-      y = channel_reduce<LPC>(y);
-      if (t.ok && t.q == 0) yrow[(long long)(4 * j + i) * ystride] = fmaf(t.Dv, u[i], y);
-    } else {
-      t.sumdl += dl[i];
-    }
-#pragma unroll
-    for (int s = 0; s < SPT; ++s) a_cur[s] = a_nxt[s];
-  }
-}
-
-template <int N, int LPC, int RP, bool WITH_Y, bool REV>
-__device__ __forceinline__ void scan_tile(Ss2dThread<N / LPC, RP> &t, const float *sXC, const float *sDB, const float *sDC,
+template <int N, int CPT, int RP, bool WITH_Y, bool REV>
+__device__ __forceinline__ void scan_tile(Ss2dThread<N, CPT, RP> &t, const float *sXC, const float *sDB, const float *sDC,
                                           float *yrow, long long ystride, int DT, int npos) {
   const int nfull = npos >> 2, rem = npos & 3;
-  float dl[4], u[4];
+  const int ycs = DT / CPT;
+  float dl[CPT][4], u[CPT][4];
   if (REV && rem) {  // the ragged group comes first when walking backwards
-    group_prologue<N, LPC, RP>(t, sXC, sDB, DT, nfull, dl, u);
-    group_body<N, LPC, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
+    group_prologue<N, CPT, RP>(t, sXC, sDB, DT, nfull, dl, u);
+    group_body<N, CPT, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, ycs, nfull, dl, u, rem);
   }
   if (nfull > 0) {
     int j = REV ? nfull - 1 : 0;
-    group_prologue<N, LPC, RP>(t, sXC, sDB, DT, j, dl, u);
-    float a_cur[N / LPC];
-#pragma unroll
-    for (int s = 0; s < N / LPC; ++s) a_cur[s] = ex2(dl[REV ? 3 : 0] * t.a2[s]);
+    group_prologue<N, CPT, RP>(t, sXC, sDB, DT, j, dl, u);
 #pragma unroll 1
     for (int g = 0; g < nfull; ++g) {
       // next group's delta'/u first (clamped index: the last iteration recomputes a valid group, unused),
       // so its loads / dot products / softplus overlap this group's exponentials and fma chains
       const int jn = REV ? max(j - 1, 0) : min(j + 1, nfull - 1);
-      float dln[4], un[4];
-      group_prologue<N, LPC, RP>(t, sXC, sDB, DT, jn, dln, un);
-      group_body_pipe<N, LPC, RP, WITH_Y, REV>(t, sDB, sDC, yrow, ystride, j, dl, u, dln[REV ? 3 : 0], a_cur);
+      float dln[CPT][4], un[CPT][4];
+      group_prologue<N, CPT, RP>(t, sXC, sDB, DT, jn, dln, un);
+      group_body<N, CPT, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, ycs, j, dl, u, 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) { dl[i] = dln[i]; u[i] = un[i]; }
+      for (int c = 0; c < CPT; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { dl[c][i] = dln[c][i]; u[c][i] = un[c][i]; }
       j = REV ? j - 1 : j + 1;
     }
   }
   if (!REV && rem) {
-    group_prologue<N, LPC, RP>(t, sXC, sDB, DT, nfull, dl, u);
-    group_body<N, LPC, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, nfull, dl, u, rem);
+    group_prologue<N, CPT, RP>(t, sXC, sDB, DT, nfull, dl, u);
+    group_body<N, CPT, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, ycs, nfull, dl, u, rem);
   }
 }
 
-template <int N, int LPC, int RP, int MODE>
-__global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+template <int N, int CPT, int RP, int MODE>
+__global__ void __launch_bounds__(160) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
 
@@ -226,9 +183,8 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
   const bool cross = p.kind == SIGMA_DIRS_CROSS;
 
   const int tid = threadIdx.x;
-  constexpr int SPT = N / LPC;               // states per thread
   const int NTC = blockDim.x - 32;           // consumer threads; the last warp is the TMA producer
-  const int DT = NTC / LPC;                  // channels per CTA
+  const int DT = NTC * CPT;                  // channels per CTA: thread t owns channels t and t + NTC (CPT = 2)
   const int nwarps_c = NTC >> 5;
   const bool is_producer = tid >= NTC;
   const int xc_fl = LT * DT, dbl_fl = LT * Cp;
@@ -236,13 +192,7 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
   uint64_t *full = reinterpret_cast<uint64_t *>(stages + NST * stage_fl);
   uint64_t *empty = full + NST;
 
-  Ss2dThread<SPT, RP> t;
-  t.lane = tid & 31;
-  t.q = tid % LPC;
-  t.ch = tid / LPC;
   const int d0 = blockIdx.x * DT;
-  const int d = d0 + t.ch;
-  t.ok = !is_producer && d < p.D;
   const int k = cross ? 0 : blockIdx.y / p.nsplit;
   const int split = cross ? blockIdx.y : blockIdx.y - k * p.nsplit;
   const int b = blockIdx.z;
@@ -290,27 +240,35 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
     return;
   }
 
-  // ===== consumer warps: one channel per thread =====
-  const long long wd = (long long)kw * p.D + (t.ok ? d : 0);
+  // ===== consumer warps: CPT channels per thread, all N states of each in registers =====
+  Ss2dThread<N, CPT, RP> t;
+  t.ch = tid;
+  float *carry_row[CPT];
 #pragma unroll
-  for (int s = 0; s < SPT; ++s) {
-    t.a2[s] = t.ok ? p.A[wd * N + t.q * SPT + s] * kLog2e : 0.f;
-    t.h[s] = 0.f;
-  }
+  for (int c = 0; c < CPT; ++c) {
+    const int d = d0 + tid + c * NTC;
+    t.ok[c] = d < p.D;
+    const long long wd = (long long)kw * p.D + (t.ok[c] ? d : 0);
 #pragma unroll
-  for (int r = 0; r < RP; ++r) t.W[r] = (t.ok && r < p.R) ? p.dtw[wd * p.R + r] : 0.f;
-  t.bias = t.ok ? p.dtb[wd] : 0.f;
-  t.Dv = t.ok ? p.Ds[wd] : 0.f;
-  t.sumdl = 0.f;
-  float *carry_row = nullptr;
-  if (MODE != MODE_SERIAL) {
-    carry_row = p.carry + ((((long long)b * p.ndir + k) * p.D + (t.ok ? d : 0)) * p.nsplit + split) * 2 * N;
-    if (MODE == MODE_APPLY && t.ok) {
+    for (int s = 0; s < N; ++s) {
+      t.a2[c][s] = t.ok[c] ? p.A[wd * N + s] * kLog2e : 0.f;
+      t.h[c][s] = 0.f;
+    }
 #pragma unroll
-      for (int s = 0; s < SPT; ++s) t.h[s] = carry_row[N + t.q * SPT + s];
+    for (int r = 0; r < RP; ++r) t.W[c][r] = (t.ok[c] && r < p.R) ? p.dtw[wd * p.R + r] : 0.f;
+    t.bias[c] = t.ok[c] ? p.dtb[wd] : 0.f;
+    t.Dv[c] = t.ok[c] ? p.Ds[wd] : 0.f;
+    t.sumdl[c] = 0.f;
+    carry_row[c] = nullptr;
+    if (MODE != MODE_SERIAL) {
+      carry_row[c] = p.carry + ((((long long)b * p.ndir + k) * p.D + (t.ok[c] ? d : 0)) * p.nsplit + split) * 2 * N;
+      if (MODE == MODE_APPLY && t.ok[c]) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) t.h[c][s] = carry_row[c][N + s];
+      }
     }
   }
-  float *ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + (t.ok ? d : 0);
+  float *ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + min(d0 + tid, p.D - 1);
   const long long istride = p.istride[k], ostride = p.ostride[k];
 
   for (int tau = t0; tau < t1; ++tau) {
@@ -326,25 +284,30 @@ __global__ void __launch_bounds__(288) ss2d_scan_kernel(const __grid_constant__ 
     const int npos = min(LT, I - i0);
     float *yrow = ybase + (long long)o * ostride + (long long)i0 * istride;
 
-    if (rev) scan_tile<N, LPC, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
-    else     scan_tile<N, LPC, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
+    if (rev) scan_tile<N, CPT, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
+    else     scan_tile<N, CPT, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
 
     __syncwarp();
     if ((tid & 31) == 0) mbar_arrive(&empty[st]);   // this warp is done with ring slot st
   }
 
-  if (MODE == MODE_SUMMARY && t.ok) {
+  if (MODE == MODE_SUMMARY) {
 #pragma unroll
-    for (int s = 0; s < SPT; ++s) {
-      carry_row[t.q * SPT + s] = ex2(t.a2[s] * t.sumdl);
-      carry_row[N + t.q * SPT + s] = t.h[s];
+    for (int c = 0; c < CPT; ++c) {
+      if (t.ok[c]) {
+#pragma unroll
+        for (int s = 0; s < N; ++s) {
+          carry_row[c][s] = ex2(t.a2[c][s] * t.sumdl[c]);
+          carry_row[c][N + s] = t.h[c][s];
+        }
+      }
     }
   }
 }
 
-// host-side launcher for one (N, LPC, RP) instantiation; defined per RP in ss2d_scan_rp*.cu.
-// `nthreads` = consumer threads per CTA (LPC per channel); the launcher adds the producer warp.
-template <int N, int LPC, int RP>
+// host-side launcher for one (N, CPT, RP) instantiation; defined per RP in ss2d_scan_rp*.cu.
+// `nthreads` = consumer threads per CTA (each owning CPT channels); the launcher adds the producer warp.
+template <int N, int CPT, int RP>
 int ss2d_launch(const Ss2dParams &p, int nthreads, cudaStream_t stream);
 
 }  // namespace sigma

@@ -55,17 +55,17 @@ static int pad_rp(int R) {
   return -1;
 }
 
-template <int N, int LPC>
+template <int N, int CPT>
 static int dispatch_rp(const Ss2dParams &p, int nthreads, cudaStream_t s) {
   switch (pad_rp(p.R)) {
-    case 4: return ss2d_launch<N, LPC, 4>(p, nthreads, s);
-    case 8: return ss2d_launch<N, LPC, 8>(p, nthreads, s);
-    case 12: return ss2d_launch<N, LPC, 12>(p, nthreads, s);
-    case 16: return ss2d_launch<N, LPC, 16>(p, nthreads, s);
-    case 24: return ss2d_launch<N, LPC, 24>(p, nthreads, s);
-    case 32: return ss2d_launch<N, LPC, 32>(p, nthreads, s);
-    case 48: return ss2d_launch<N, LPC, 48>(p, nthreads, s);
-    case 64: return ss2d_launch<N, LPC, 64>(p, nthreads, s);
+    case 4: return ss2d_launch<N, CPT, 4>(p, nthreads, s);
+    case 8: return ss2d_launch<N, CPT, 8>(p, nthreads, s);
+    case 12: return ss2d_launch<N, CPT, 12>(p, nthreads, s);
+    case 16: return ss2d_launch<N, CPT, 16>(p, nthreads, s);
+    case 24: return ss2d_launch<N, CPT, 24>(p, nthreads, s);
+    case 32: return ss2d_launch<N, CPT, 32>(p, nthreads, s);
+    case 48: return ss2d_launch<N, CPT, 48>(p, nthreads, s);
+    case 64: return ss2d_launch<N, CPT, 64>(p, nthreads, s);
   }
   set_error("sigma_ss2d_scan_fwd: dt_rank %d > 64 unsupported", p.R);
   return SIGMA_EUNSUPPORTED;
@@ -74,14 +74,14 @@ static int dispatch_rp(const Ss2dParams &p, int nthreads, cudaStream_t s) {
 static int kind_dirs(int kind) { return kind == SIGMA_DIRS_CROSS4 ? 4 : (kind == SIGMA_DIRS_SEQ2 ? 2 : 1); }
 static int lt_for(int N) { return N >= 16 ? Ss2dCfg<16>::LT : Ss2dCfg<4>::LT; }
 
-// consumer warps per CTA: the largest count <= maxw whose channel tile (32/LPC channels per warp) divides D;
-// ragged D falls back to enough warps to cover it with a partially filled last CTA (TMA zero-fills, stores
-// are predicated)
-static int pick_warps(int D, int lpc, int maxw) {
-  const int cpw = 32 / lpc;
+// consumer warps per CTA: the largest count <= maxw whose channel tile (32·cpt channels per warp) divides D;
+// ragged D falls back to enough warps to cover it with a partially filled last CTA (TMA zero-fills, stores are
+// predicated)
+static int pick_warps(int D, int cpt, int maxw) {
+  const int cpw = 32 * cpt;
   for (int w = maxw; w >= 1; --w)
     if (D % (cpw * w) == 0) return w;
-  return std::min(maxw, (D + cpw - 1) / cpw);
+  return std::max(1, std::min(maxw, (D + cpw - 1) / cpw));
 }
 
 constexpr int kMaxSplit = 32;
@@ -103,19 +103,17 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   const long long Lseq = kind == SIGMA_DIRS_SEQ2 ? 2LL * H * W : (long long)H * W;
   p.Lseq = Lseq;
   const int LT = lt_for(N);
-  // lanes per channel: more lanes = more warps for the same work (needed when batch x K x D/32 warps cannot
-  // fill the 592 SM sub-partitions), fewer lanes = fewer instructions per element.  SIGMA_SCAN_LPC overrides.
-  const long long warps1 = (long long)batch * ndir * ((D + 31) / 32);
-  int lpc = 1;
-  if (N == 16) lpc = warps1 >= 148LL * 4 * 4 ? 1 : (warps1 >= 148LL * 4 * 2 ? 2 : 4);
-  else if (N == 8) lpc = warps1 >= 148LL * 4 * 2 ? 1 : 2;
-  if (const char *e = getenv("SIGMA_SCAN_LPC")) {
+  // channels per thread: 2 halves the B/C shared-memory traffic and the address arithmetic per channel (the scan's
+  // co-bottleneck next to the MUFU), 1 doubles the number of warps when batch x K x D is small.
+  const long long warps2 = (long long)batch * ndir * ((D + 63) / 64);
+  int cpt = warps2 >= 148LL * 4 ? 2 : 1;
+  if (const char *e = getenv("SIGMA_SCAN_CPT")) {
     const int v = atoi(e);
-    if ((v == 1 || v == 2 || v == 4) && N % (4 * v) == 0) lpc = v;
+    if (v == 1 || v == 2) cpt = v;
   }
-  int maxw = 4;  // 4 consumer warps + 1 producer per CTA measured best on B200 (profiles/r01_scan_variants.txt)
-  if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(8, atoi(e)));
-  const int NW = pick_warps(D, lpc, maxw), DT = (32 / lpc) * NW;
+  int maxw = 4;  // <= 4 consumer warps + 1 producer per CTA measured best on B200 (profiles/r01_scan_variants.txt)
+  if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(4, atoi(e)));
+  const int NW = pick_warps(D, cpt, maxw), DT = 32 * cpt * NW;
   int rc;
   int max_tiles = 0;
   for (int k = 0; k < ndir; ++k) {
@@ -165,13 +163,13 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   p.nsplit = nsplit;
 
   const int nthreads = 32 * NW;
-  switch (N * 8 + lpc) {
+  switch (N * 8 + cpt) {
     case 4 * 8 + 1: return dispatch_rp<4, 1>(p, nthreads, stream);
+    case 4 * 8 + 2: return dispatch_rp<4, 2>(p, nthreads, stream);
     case 8 * 8 + 1: return dispatch_rp<8, 1>(p, nthreads, stream);
     case 8 * 8 + 2: return dispatch_rp<8, 2>(p, nthreads, stream);
     case 16 * 8 + 1: return dispatch_rp<16, 1>(p, nthreads, stream);
     case 16 * 8 + 2: return dispatch_rp<16, 2>(p, nthreads, stream);
-    case 16 * 8 + 4: return dispatch_rp<16, 4>(p, nthreads, stream);
   }
   set_error("sigma_ss2d_scan_fwd: d_state=%d unsupported by the fused kernel (4, 8, 16)", N);
   return SIGMA_EUNSUPPORTED;
