@@ -106,13 +106,14 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   // channels per thread: 2 halves the B/C shared-memory traffic and the address arithmetic per channel (the scan's
   // co-bottleneck next to the MUFU), 1 doubles the number of warps when batch x K x D is small.
   const long long warps2 = (long long)batch * ndir * ((D + 63) / 64);
-  int cpt = warps2 >= 148LL * 4 * 6 ? 2 : 1;   // measured: CPT=2 only pays once >= ~6 warps/sub-partition remain
+  int cpt = 1;   // measured (profiles/r01_scan_variants.txt): CPT=2 loses at every Sigma shape up to 32 images/GPU
+  (void)warps2;
   if (const char *e = getenv("SIGMA_SCAN_CPT")) {
     const int v = atoi(e);
     if (v == 1 || v == 2) cpt = v;
   }
   int maxw = 4;  // <= 4 consumer warps + 1 producer per CTA measured best on B200 (profiles/r01_scan_variants.txt)
-  if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(8, atoi(e)));
+  if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(4, atoi(e)));
   const int NW = pick_warps(D, cpt, maxw), DT = 32 * cpt * NW;
   int rc;
   int max_tiles = 0;
