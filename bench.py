@@ -180,40 +180,47 @@ def scan_algo_bytes(kind, batch, H, W, D, N):
     return 4 * (3 * Bn * KD * L + 2 * Bn * K * N * L) + 4 * (KD * N + 2 * KD)
 
 
-def measure_roofline(model, rgb, mx, passes=3):
-    """Eager (un-graphed) passes with CUDA events around every fused-scan call on the launching stream."""
+def measure_roofline(model, rgb, mx, reps=3):
+    """Kernel time of every fused-scan call of one forward, measured live with CUDA events on the launching stream:
+    the calls (with their real inputs) are recorded during one eager forward, then each is replayed `reps` times
+    back to back between two events after an L2 flush, so the interval contains kernel execution only (in the eager
+    forward itself the host-side launch work of a call would sit between the events)."""
     from sigma_b200 import fused
-    rec = []
+    calls = []
     orig = fused.ss2d_scan
 
-    def timed(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        y = orig(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp)
-        e1.record()
-        rec.append((scan_algo_bytes(kind, batch, H, W, D, N), N, e0, e1))
-        return y
+    def record(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
+        calls.append((kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp))
+        return orig(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp)
 
-    fused.ss2d_scan = timed
+    fused.ss2d_scan = record
     try:
         with torch.no_grad():
-            model(rgb, mx)          # warm
-            torch.cuda.synchronize()
-            rec.clear()
-            for _ in range(passes):
-                model(rgb, mx)
-            torch.cuda.synchronize()
+            model(rgb, mx)
+        torch.cuda.synchronize()
     finally:
         fused.ss2d_scan = orig
-    tot_b = sum(r[0] for r in rec)
-    tot_ms = sum(r[2].elapsed_time(r[3]) for r in rec)
-    by_n = {}
-    for b, n, e0, e1 in rec:
-        s = by_n.setdefault(n, [0, 0.0, 0])
-        s[0] += b
-        s[1] += e0.elapsed_time(e1)
-        s[2] += 1
-    return tot_b, tot_ms, len(rec), passes, by_n
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=rgb.device)
+    tot_b, tot_ms, by_n = 0, 0.0, {}
+    for c in calls:
+        orig(*c)                                  # warm (allocator, attributes)
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            orig(*c)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        b = scan_algo_bytes(c[0], c[7], c[8], c[9], c[10], c[11])
+        tot_b += b
+        tot_ms += ms
+        s_ = by_n.setdefault(c[11], [0, 0.0, 0])
+        s_[0] += b
+        s_[1] += ms
+        s_[2] += 1
+    return tot_b, tot_ms, len(calls), 1, by_n
 
 
 # ------------------------------------------------------------------ main arm

@@ -43,6 +43,7 @@ struct alignas(64) Ss2dParams {
   int I[4], O[4], rev[4];
   long long istride[4], ostride[4];   // y element strides of the inner / outer walk index
   int nsplit, tiles_per_split;
+  int ablate;  // timing experiments only (SIGMA_SCAN_ABLATE): 1 = no y store, 2 = no per-group prologue, 4 = no TMA reload
 };
 
 __host__ __device__ inline size_t ss2d_smem_bytes(int LT, int DT, int NST, int Cp, bool cross) {
@@ -55,6 +56,7 @@ struct Ss2dThread {
   float h[CPT][N], a2[CPT][N], W[CPT][RP];
   float bias[CPT], Dv[CPT], sumdl[CPT];
   int ch;          // first channel of this thread inside the CTA tile; the c-th is ch + c*DT/CPT
+  int ablate;
   bool ok[CPT];
 };
 
@@ -129,7 +131,8 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
       for (int c = 0; c < CPT; ++c) {
         if (WITH_Y) {
           const float y = (yacc[c][0].x + yacc[c][0].y) + (yacc[c][1].x + yacc[c][1].y);
-          if (t.ok[c]) yrow[(long long)(4 * j + i) * ystride + c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
+          if (t.ok[c] && !(t.ablate & 1)) yrow[(long long)(4 * j + i) * ystride + c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
+          if (t.ablate & 1) t.sumdl[c] += y;
         } else {
           t.sumdl[c] += dl[c][i];
         }
@@ -157,7 +160,13 @@ __device__ __forceinline__ void scan_tile(Ss2dThread<N, CPT, RP> &t, const float
       // so its loads / dot products / softplus overlap this group's exponentials and fma chains
       const int jn = REV ? max(j - 1, 0) : min(j + 1, nfull - 1);
       float dln[CPT][4], un[CPT][4];
-      group_prologue<N, CPT, RP>(t, sXC, sDB, DT, jn, dln, un);
+      if (!(t.ablate & 2)) group_prologue<N, CPT, RP>(t, sXC, sDB, DT, jn, dln, un);
+      else {
+#pragma unroll
+        for (int c = 0; c < CPT; ++c)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
+      }
       group_body<N, CPT, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, ycs, j, dl, u, 4);
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__(160) ss2d_scan_kernel(const __grid_constant__ 
       const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
       for (int tau = t0; tau < t1; ++tau) {
         const int it = tau - t0, st = it % NST;
+        if ((p.ablate & 4) && it >= NST) break;
         mbar_wait(&empty[st], (uint32_t)(((it / NST) & 1) ^ 1));   // fresh barrier: parity 1 passes immediately
         float *dst = stages + st * stage_fl;
         int o, i0;
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__(160) ss2d_scan_kernel(const __grid_constant__ 
   // ===== consumer warps: CPT channels per thread, all N states of each in registers =====
   Ss2dThread<N, CPT, RP> t;
   t.ch = tid;
+  t.ablate = p.ablate;
   float *carry_row[CPT];
 #pragma unroll
   for (int c = 0; c < CPT; ++c) {
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(160) ss2d_scan_kernel(const __grid_constant__ 
   for (int tau = t0; tau < t1; ++tau) {
     const int it = tau - t0;
     const int st = it % NST;
-    mbar_wait(&full[st], (uint32_t)((it / NST) & 1));
+    if (!((p.ablate & 4) && it >= NST)) mbar_wait(&full[st], (uint32_t)((it / NST) & 1));
 
     const float *sXC = stages + st * stage_fl;
     const float *sDB = sXC + xc_fl;
@@ -288,13 +299,13 @@ __global__ void __launch_bounds__(160) ss2d_scan_kernel(const __grid_constant__ 
     else     scan_tile<N, CPT, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
 
     __syncwarp();
-    if ((tid & 31) == 0) mbar_arrive(&empty[st]);   // this warp is done with ring slot st
+    if ((tid & 31) == 0 && !(p.ablate & 4)) mbar_arrive(&empty[st]);   // this warp is done with ring slot st
   }
 
-  if (MODE == MODE_SUMMARY) {
+  if (MODE == MODE_SUMMARY || (p.ablate & 1)) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-      if (t.ok[c]) {
+      if (t.ok[c] && carry_row[c] != nullptr) {
 #pragma unroll
         for (int s = 0; s < N; ++s) {
           carry_row[c][s] = ex2(t.a2[c][s] * t.sumdl[c]);
