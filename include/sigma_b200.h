@@ -164,6 +164,17 @@ int sigma_pool_avgmax_partial_fwd(const float *x, float *partial, int batch, int
 int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const float *sb, float *out, int64_t rows,
                         int64_t rows_per_batch, int C, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Dense projections (in_proj / x_proj / out_proj / PatchMerging / PatchExpand / decoder linears,
+ * vmamba.py:679,725,616,195; MambaDecoder.py:17,39,82-83): hand-written tcgen05 (5th-gen tensor core) TF32 GEMM,
+ * fp32 storage, fp32 accumulate in TMEM, TMA-fed, fused epilogue:
+ *     C[M,N] = A[M,K]·W[N,K]^T (+ bias[N]) (+ residual[M,N] (· rscale[N]))
+ * A rows lda floats apart, W (N,K) contiguous, C rows ldc apart, residual rows ldr apart; K, lda, ldc, ldr % 4 == 0.
+ * rscale is the per-channel residual scale of CVSSDecoderBlock (vmamba.py:1801); bias/residual/rscale nullable.
+ * ------------------------------------------------------------------------------------------ */
+int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *bias, const float *residual, int64_t ldr,
+                      const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

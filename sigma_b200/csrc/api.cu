@@ -212,6 +212,8 @@ int upsample2x_norm_launch(const float *in, const float *gamma, const float *bet
 int pool_avgmax_partial_launch(const float *x, float *partial, int B, long long L, int C, int nslice, cudaStream_t stream);
 int scale_add_launch(const float *a, const float *sa, const float *b, const float *sb, float *out, long long rows,
                      long long rows_per_batch, int C, cudaStream_t stream);
+int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *bias, const float *residual, long long ldr,
+                     const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream);
 static bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace sigma
 
@@ -389,6 +391,18 @@ int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void 
   }
   if ((rc = cast_out<__nv_bfloat16>(du32, du, batch, dim, seqlen, sb, seqlen, stream))) return rc;
   return cast_out<__nv_bfloat16>(dd32, ddelta, batch, dim, seqlen, sb, seqlen, stream);
+}
+
+int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *bias, const float *residual, int64_t ldr,
+                      const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream) {
+  SIGMA_CHECK_ARG(A && W && C, "sigma_linear_tf32: null pointer");
+  SIGMA_CHECK_ARG(M >= 0 && M < (1LL << 31) && N > 0 && K > 0, "sigma_linear_tf32: bad sizes M=%lld N=%d K=%d", (long long)M, N, K);
+  SIGMA_CHECK_ARG(K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && (residual == nullptr || ldr % 4 == 0) && lda >= K && ldc >= N,
+                  "sigma_linear_tf32: K, lda, ldc, ldr must be multiples of 4 floats (16-byte TMA / vector alignment)");
+  SIGMA_CHECK_ARG(al16(A) && al16(W) && al16(C) && al16(bias) && al16(residual) && al16(rscale),
+                  "sigma_linear_tf32: pointers must be 16-byte aligned");
+  SIGMA_CHECK_ARG(rscale == nullptr || residual != nullptr, "sigma_linear_tf32: rscale without residual");
+  return gemm_tf32_launch(A, lda, W, bias, residual, ldr, rscale, C, ldc, M, N, K, (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop

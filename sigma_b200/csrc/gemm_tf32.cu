@@ -1,0 +1,251 @@
+// Dense projections of the hot path (in_proj / x_proj / out_proj / PatchMerging / PatchExpand / decoder linears,
+// vmamba.py:679,195,725,616; MambaDecoder.py:17,39,82-83) as ONE hand-written sm_100a GEMM:
+//
+//     C[M,N] = A[M,K] · W[N,K]^T  (+ bias[N])  (+ residual[M,N] · rscale[N])      fp32 in / fp32 out
+//
+// 5th-generation tensor cores: `tcgen05.mma.cta_group::1.kind::tf32` issued by one elected thread, fp32 operands
+// read as TF32 straight from shared memory (no conversion pass), fp32 accumulators in TMEM, operand tiles staged
+// by TMA (128-byte swizzle) through a full/empty mbarrier ring, accumulators read back with `tcgen05.ld` and the
+// bias / residual epilogue fused before the store.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer, warps 2-5 = epilogue (each owns the TMEM lane quarter `warp % 4`).
+// One CTA per 128 x BN output tile; BN (<= 256, multiple of 16) is a runtime value chosen per call.
+// These GEMMs are HBM-bound at the Sigma shapes (K = 96..1536): what matters is one pass over A and one over C.
+#include <algorithm>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace sigma {
+
+constexpr int GM_BM = 128;   // rows per CTA tile = UMMA_M
+constexpr int GM_BK = 32;    // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int GM_UK = 8;     // UMMA_K for kind::tf32 (32 bytes)
+
+struct alignas(64) GemmParams {
+  CUtensorMap m_a, m_w;
+  const float *bias, *residual, *rscale;
+  float *C;
+  long long ldr, ldc;
+  int M, N, K, BN, stages, tmem_cols;
+};
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// K-major, 128-byte-swizzled operand tile: rows are 128 B apart, 8-row groups 1024 B apart (SBO), descriptor
+// version 1 (Blackwell), layout type 2 = SWIZZLE_128B.  Advancing along K inside the swizzle row = +32 B on the
+// start address per UMMA_K.
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
+  const uint32_t addr = smem_u32(smem);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);          // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                          // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D = fp32 (c_format 1), A = B = TF32 (format 2), both K-major, N >> 3, M >> 4
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const int BN = p.BN, S = p.stages;
+  const int a_bytes = GM_BM * GM_BK * 4, b_bytes = BN * GM_BK * 4;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
+  uint64_t *empty = full + S;
+  uint64_t *accum_full = empty + S;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_BM;
+  const int nkb = (p.K + GM_BK - 1) / GM_BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.m_a);
+    tma_prefetch_desc(&p.m_w);
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % S;
+        mbar_wait(&empty[st], (uint32_t)(((kb / S) & 1) ^ 1));
+        unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
+        mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + b_bytes));
+        tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);
+        tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kb * GM_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread drives the tensor core =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(GM_BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb % S;
+        mbar_wait(&full[st], (uint32_t)((kb / S) & 1));
+        tc_fence_after();
+        const unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
+        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+#pragma unroll
+        for (int k = 0; k < GM_BK / GM_UK; ++k)   // +32 B along K inside the swizzle row = +2 in 16-byte units
+          umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        umma_commit(&empty[st]);                   // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(accum_full);                     // accumulator complete
+    }
+  } else {
+    // ===== epilogue warps: TMEM -> registers -> (+bias, +residual·rscale) -> global =====
+    const int quarter = warp & 3;                  // TMEM lanes 32·quarter .. +31 are accessible to this warp
+    const int row = m0 + quarter * 32 + lane;
+    mbar_wait(accum_full, 0);
+    tc_fence_after();
+    const bool row_ok = row < p.M;
+    float *crow = p.C + (long long)row * p.ldc;
+    const float *rrow = p.residual ? p.residual + (long long)row * p.ldr : nullptr;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);   // warp-wide: executed by all lanes
+      const int n = n0 + c0;
+      if (row_ok && n < p.N) {
+        if (n + 16 <= p.N) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + q);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (rrow) {
+              const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow + n) + q);
+              if (p.rscale) {
+                const float4 s = __ldg(reinterpret_cast<const float4 *>(p.rscale + n) + q);
+                o.x = fmaf(r.x, s.x, o.x); o.y = fmaf(r.y, s.y, o.y); o.z = fmaf(r.z, s.z, o.z); o.w = fmaf(r.w, s.w, o.w);
+              } else {
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+            }
+            reinterpret_cast<float4 *>(crow + n)[q] = o;
+          }
+        } else {
+          for (int i = 0; i < 16 && n + i < p.N; ++i) {
+            float o = v[i];
+            if (p.bias) o += p.bias[n + i];
+            if (rrow) o = p.rscale ? fmaf(rrow[n + i], p.rscale[n + i], o) : o + rrow[n + i];
+            crow[n + i] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host ----
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+void *get_tensor_map_encoder();  // ss2d_scan_host.cu
+
+static int make_tmap_2d_sw128(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn2 fn = (EncodeTiledFn2)get_tensor_map_encoder();
+  if (!fn) return SIGMA_ECUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t bdim[2] = {(cuuint32_t)GM_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (gemm operand) failed (CUresult %d): rows=%lld cols=%lld ld=%lld box_rows=%d base=%p",
+              (int)r, rows, cols, ld, box_rows, (const void *)base);
+    return SIGMA_ECUDA;
+  }
+  return SIGMA_OK;
+}
+
+static int pick_bn(int N) {
+  if (N <= 256 && N % 16 == 0) return N;
+  for (int bn = 256; bn >= 64; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 128;  // ragged N: the last tile is masked (TMA zero-fills the missing rows of W)
+}
+
+int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *bias, const float *residual, long long ldr,
+                     const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream) {
+  if (M == 0) return SIGMA_OK;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.bias = bias; p.residual = residual; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
+  p.M = (int)M; p.N = N; p.K = K;
+  p.BN = pick_bn(N);
+  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  int rc;
+  if ((rc = make_tmap_2d_sw128(&p.m_a, A, M, K, lda, GM_BM))) return rc;
+  if ((rc = make_tmap_2d_sw128(&p.m_w, W, N, K, K, p.BN))) return rc;
+  const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
+  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  const int nkb = (K + GM_BK - 1) / GM_BK;
+  p.stages = std::max(2, std::min(std::min(6, nkb), (100 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16;
+  SIGMA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((N + p.BN - 1) / p.BN, (unsigned)((M + GM_BM - 1) / GM_BM));
+  gemm_tf32_kernel<<<grid, 192, smem, stream>>>(p);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+}  // namespace sigma

@@ -26,6 +26,8 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+void *get_tensor_map_encoder() { return (void *)get_encode_fn(); }
+
 int make_tmap_f32_4d(CUtensorMap *map, const void *base, const uint64_t dims[4], const uint64_t strides_bytes[3],
                      const uint32_t box[4]) {
   EncodeTiledFn fn = get_encode_fn();

@@ -36,14 +36,29 @@ def layernorm(x2d, ln):
     return y
 
 
-def linear(x2d, weight, bias=None, out=None):
-    """Dense projection y = x·W^T (+b).  Plain library GEMM (cuBLAS through torch) in this round; the
-    tcgen05/TMEM replacement slots in here."""
+USE_TCGEN05_GEMM = True  # False: cuBLAS TF32 through torch (library GEMM), kept for A/B timing only
+
+
+def linear(x2d, weight, bias=None, out=None, residual=None, rscale=None):
+    """Dense projection out = x·W^T (+bias) (+residual·rscale) through the hand-written tcgen05 TF32 GEMM
+    (csrc/gemm_tf32.cu: TMA-fed, TMEM accumulators, fused epilogue).  x2d (M, K) with unit column stride, row
+    stride % 4 == 0; weight (N, K) contiguous."""
+    M, K = x2d.shape
+    N = weight.shape[0]
     if out is None:
-        return F.linear(x2d, weight, bias)
-    torch.mm(x2d, weight.t(), out=out)
-    if bias is not None:
-        out += bias
+        out = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
+    if not USE_TCGEN05_GEMM or K % 4 or x2d.stride(1) != 1 or x2d.stride(0) % 4 or N % 4:
+        torch.mm(x2d, weight.t(), out=out)
+        if bias is not None:
+            out += bias
+        if residual is not None:
+            out += residual * rscale if rscale is not None else residual
+        return out
+    w = weight if weight.is_contiguous() else weight.contiguous()
+    ldr = residual.stride(0) if residual is not None else 0
+    rc = _lib.lib().sigma_linear_tf32(_p(x2d), x2d.stride(0), _p(w), _p(bias), _p(residual), ldr, _p(rscale), _p(out),
+                                      out.stride(0), M, N, K, _stream())
+    _lib.check(rc, "sigma_linear_tf32")
     return out
 
 
@@ -133,8 +148,9 @@ def _cma_params(cm):
 
 
 # ---------------------------------------------------------------- blocks
-def ss2d(m, x, residual=None):
-    """SS2D.forward (vmamba.py:1067-1089); x (B,H,W,C) contiguous.  Returns (B,H,W,C) [+ residual]."""
+def ss2d(m, x, residual=None, rscale=None):
+    """SS2D.forward (vmamba.py:1067-1089); x (B,H,W,C) contiguous.  Returns (B,H,W,C) [+ residual (· rscale)], the
+    residual being added in the out_proj GEMM epilogue."""
     x = x.contiguous()
     B, H, W, C = x.shape
     D, N, R, L = m.d_inner, m.d_state, m.dt_rank, H * W
@@ -147,8 +163,8 @@ def ss2d(m, x, residual=None):
     yg = torch.empty((B * L, D), dtype=torch.float32, device=x.device)
     z = ctypes.c_void_p(xz.data_ptr() + 4 * D)
     merge_norm_gate(y, 4, B * L * D, 0, m.out_norm, z, 2 * D, None, yg, 0, D, B * L, B * L, D)
-    out = linear(yg, m.out_proj.weight, m.out_proj.bias).view(B, H, W, C)
-    return out if residual is None else residual + out
+    res2d = residual.reshape(B * L, C) if residual is not None else None
+    return linear(yg, m.out_proj.weight, m.out_proj.bias, residual=res2d, rscale=rscale).view(B, H, W, C)
 
 
 def vss_block(blk, x):
@@ -191,9 +207,11 @@ def cromb_ss2d(m, x_rgb, x_e, residual=False):
     yn = torch.empty((2, B * L, D), dtype=torch.float32, device=dev)
     merge_norm_gate(y, 1, 0, 0, cm.out_norm_1, None, 0, None, yn, 0, D, B * L, B * L, D)
     merge_norm_gate(y, 1, 0, 0, cm.out_norm_2, None, 0, None, yn, 0, D, B * L, B * L, D, y_offset=B * L * D, out_offset=B * L * D)
-    o_r = linear(yn[0], m.out_proj_rgb.weight, m.out_proj_rgb.bias).view(B, H, W, C)
-    o_e = linear(yn[1], m.out_proj_e.weight, m.out_proj_e.bias).view(B, H, W, C)
-    return (x_rgb + o_r, x_e + o_e) if residual else (o_r, o_e)
+    r_r = x_rgb.view(B * L, C) if residual else None
+    r_e = x_e.view(B * L, C) if residual else None
+    o_r = linear(yn[0], m.out_proj_rgb.weight, m.out_proj_rgb.bias, residual=r_r).view(B, H, W, C)
+    o_e = linear(yn[1], m.out_proj_e.weight, m.out_proj_e.bias, residual=r_e).view(B, H, W, C)
+    return o_r, o_e
 
 
 def conmb_ss2d(m, x_rgb, x_e, residual=None):
@@ -276,7 +294,7 @@ def cvss_decoder_block(blk, x):
     x = x.contiguous()
     B, H, W, C = x.shape
     xn = layernorm(x.view(-1, C), blk.norm1).view(B, H, W, C)
-    x1 = ss2d(blk.op, xn, residual=scale_add(None, None, x, blk.scale1, H * W))
+    x1 = ss2d(blk.op, xn, residual=x, rscale=blk.scale1)            # x·scale1 + SS2D(LN(x)) in the GEMM epilogue
     xn2 = layernorm(x1.view(-1, C), blk.norm2).view(B, H, W, C)
     cab = blk.conv_blk.cab
     t = cab[2](cab[1](cab[0](xn2.permute(0, 3, 1, 2))))            # conv3x3 -> GELU -> conv3x3 on a channels_last view

@@ -176,3 +176,38 @@ def test_pool_and_scale_add():
     assert_close(got, a * sa[:, None, None, :] + bq * sb, 1e-6, 1e-6, "scale_add")
     got = fused.scale_add(None, None, bq.cuda(), sb.cuda(), H * W)
     assert_close(got, bq * sb, 1e-6, 1e-6, "scale only")
+
+
+@pytest.mark.parametrize("M,N,K,extras", [
+    (1000, 384, 96, ""), (77, 160, 192, "b"), (300, 96, 192, "r"), (513, 192, 384, "rs"), (129, 40, 64, "br"),
+    (64, 32, 16, ""), (2500, 768, 1536, "r"), (4096, 320, 1536, ""), (1, 16, 32, "b"), (700, 3072, 768, ""),
+])
+def test_tcgen05_tf32_gemm(M, N, K, extras):
+    """sigma_linear_tf32 vs fp64 matmul; tolerance = TF32 input rounding (2^-10 relative per product)."""
+    from sigma_b200 import fused
+    tag = f"gemm/{M}/{N}/{K}"
+    A = P.randn(S, tag + "/A", (M, K))
+    Wt = P.randn(S, tag + "/W", (N, K), K ** -0.5)
+    bias = P.randn(S, tag + "/b", (N,)) if "b" in extras else None
+    res = P.randn(S, tag + "/r", (M, N)) if "r" in extras else None
+    rs = P.randn(S, tag + "/s", (N,), 0.2, 1.0) if "s" in extras else None
+    ref = A.double() @ Wt.double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    if res is not None:
+        ref = ref + res.double() * (rs.double() if rs is not None else 1.0)
+    c = lambda t: None if t is None else t.cuda()
+    assert fused.USE_TCGEN05_GEMM
+    got = fused.linear(c(A), c(Wt), c(bias), residual=c(res), rscale=c(rs))
+    torch.cuda.synchronize()
+    bound = 2.5e-3 * float((A.abs().double() @ Wt.abs().double().t()).max()) + 1e-5
+    err = float((got.cpu().double() - ref).abs().max())
+    assert err < bound, f"{tag}: max abs err {err:.3e} > {bound:.3e}"
+    # strided A (the x half of [x | z] rows) and strided output
+    if K % 4 == 0 and M > 4:
+        big = torch.zeros(M, 2 * K + 4, device="cuda")
+        big[:, :K] = A.cuda()
+        out = torch.zeros(M, N + 8, device="cuda")
+        fused.linear(big[:, :K], c(Wt), None, out=out[:, :N])
+        ref2 = A.double() @ Wt.double().t()
+        assert float((out[:, :N].cpu().double() - ref2).abs().max()) < bound and float(out[:, N:].abs().max()) == 0.0
