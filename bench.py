@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--num-classes", type=int, default=9)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cublas-gemm", action="store_true", help="A/B: dense projections through cuBLAS instead of our tcgen05 GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=2)
     return ap.parse_args()
@@ -236,7 +237,9 @@ def main():
     dev = torch.device("cuda", local)
     dist_util.init("nccl", dev)
 
-    from sigma_b200 import _lib, modules as M
+    from sigma_b200 import _lib, fused, modules as M
+    if a.cublas_gemm:
+        fused.USE_TCGEN05_GEMM = False
     # dense projections run on the tensor cores in TF32 (fp32 storage, fp32 accumulate); the scan is fp32
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
@@ -373,7 +376,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"replicas x{world} (no data-path collective)", "scan_math": "fp32",
-                   "dense_math": "tf32 tensor cores, fp32 accumulate", "cuda_graph": graph is not None,
+                   "dense_math": "tf32 tensor cores (hand-written tcgen05 GEMM), fp32 accumulate" if fused.USE_TCGEN05_GEMM else "tf32 cuBLAS", "cuda_graph": graph is not None,
                    "l2": "256 MiB flush between timed steps"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": round(n_img / (e2e_ms * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,

@@ -236,8 +236,8 @@ def conmb_ss2d(m, x_rgb, x_e, residual=None):
     merge_norm_gate(y, 2, ks, 2 * L * D, m.out_norm1, None, 0, g_e, ycat, L * 2 * D, 2 * D, B * L, L, D)
     merge_norm_gate(y, 2, ks, 2 * L * D, m.out_norm2, None, 0, g_r, ycat, L * 2 * D, 2 * D, B * L, L, D,
                     y_offset=L * D, out_offset=D)
-    out = linear(ycat, m.out_proj.weight, m.out_proj.bias).view(B, H, W, C)
-    return out if residual is None else residual + out
+    res2d = residual.reshape(B * L, C) if residual is not None else None
+    return linear(ycat, m.out_proj.weight, m.out_proj.bias, residual=res2d).view(B, H, W, C)
 
 
 # ---------------------------------------------------------------- decoder pieces

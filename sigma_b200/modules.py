@@ -508,6 +508,8 @@ class ConcatMambaFusionBlock(nn.Module):
             self.mlp = Mlp(in_features=hidden_dim, hidden_features=int(hidden_dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def _forward(self, x_rgb, x_e):
+        if _fused_ok(x_rgb, x_e) and not self.mlp_branch:
+            return self.op(x_rgb, x_e, residual=x_rgb + x_e)     # the sum is added in the out_proj GEMM epilogue
         x = x_rgb + x_e + self.drop_path(self.op(x_rgb, x_e))
         if self.mlp_branch:
             x = x + self.drop_path(self.mlp(self.norm2(x)))
