@@ -8,7 +8,8 @@
 // by TMA (128-byte swizzle) through a full/empty mbarrier ring, accumulators read back with `tcgen05.ld` and the
 // bias / residual epilogue fused before the store.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
 // allocator + MMA issuer, warps 2-5 = epilogue (each owns the TMEM lane quarter `warp % 4`).
-// One CTA per 128 x BN output tile; BN (<= 256, multiple of 16) is a runtime value chosen per call.
+// Persistent CTAs loop over 128 x BN output tiles (BN <= 256, multiple of 16, a runtime value chosen per call) with
+// two TMEM accumulator stages, so the loads and MMAs of the next tile overlap the epilogue of the current one.
 // These GEMMs are HBM-bound at the Sigma shapes (K = 96..1536): what matters is one pass over A and one over C.
 #include <algorithm>
 
@@ -88,18 +89,22 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
   uint64_t *empty = full + S;
-  uint64_t *accum_full = empty + S;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_full + 1);
+  uint64_t *acc_full = empty + S;      // [2]: accumulator stage complete (MMA -> epilogue)
+  uint64_t *acc_empty = acc_full + 2;  // [2]: accumulator stage drained (epilogue -> MMA)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_BM;
   const int nkb = (p.K + GM_BK - 1) / GM_BK;
+  const int num_n = (p.N + BN - 1) / BN;
+  const int num_m = (p.M + GM_BM - 1) / GM_BM;
+  const long long total = (long long)num_m * num_n;
+  const int acc_cols = p.tmem_cols >> 1;   // columns per accumulator stage
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.m_a);
     tma_prefetch_desc(&p.m_w);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(accum_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
   }
   if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it
@@ -112,77 +117,103 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Persistent CTA: tiles blockIdx.x, +gridDim.x, ... (n fastest, so consecutive tiles re-read the same A rows from
+  // L2).  The three roles run their own loops over the same tile sequence and meet only at the mbarriers, so the
+  // TMA loads of tile i+1 and the MMAs of tile i+1 overlap the epilogue of tile i (two TMEM accumulator stages).
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % S;
-        mbar_wait(&empty[st], (uint32_t)(((kb / S) & 1) ^ 1));
-        unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
-        mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + b_bytes));
-        tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);
-        tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kb * GM_BK, n0);
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = (int)(it % S);
+          mbar_wait(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));
+          unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
+          mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + b_bytes));
+          tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);
+          tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kb * GM_BK, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: one thread drives the tensor core =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_tf32(GM_BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int st = kb % S;
-        mbar_wait(&full[st], (uint32_t)((kb / S) & 1));
+      long long it = 0, tc = 0;
+      for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+        const int acc = (int)(tc & 1);
+        mbar_wait(&acc_empty[acc], (uint32_t)(((tc >> 1) & 1) ^ 1));   // epilogue has drained this accumulator stage
         tc_fence_after();
-        const unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
-        const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int st = (int)(it % S);
+          mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+          tc_fence_after();
+          const unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
 #pragma unroll
-        for (int k = 0; k < GM_BK / GM_UK; ++k)   // +32 B along K inside the swizzle row = +2 in 16-byte units
-          umma_tf32(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-        umma_commit(&empty[st]);                   // frees the smem slot once these MMAs have read it
+          for (int k = 0; k < GM_BK / GM_UK; ++k)   // +32 B along K inside the swizzle row = +2 in 16-byte units
+            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          umma_commit(&empty[st]);                   // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&acc_full[acc]);                 // accumulator of this tile complete
       }
-      umma_commit(accum_full);                     // accumulator complete
     }
   } else {
     // ===== epilogue warps: TMEM -> registers -> (+bias, +residual·rscale) -> global =====
-    const int quarter = warp & 3;                  // TMEM lanes 32·quarter .. +31 are accessible to this warp
-    const int row = m0 + quarter * 32 + lane;
-    mbar_wait(accum_full, 0);
-    tc_fence_after();
-    const bool row_ok = row < p.M;
-    float *crow = p.C + (long long)row * p.ldc;
-    const float *rrow = p.residual ? p.residual + (long long)row * p.ldr : nullptr;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);   // warp-wide: executed by all lanes
-      const int n = n0 + c0;
-      if (row_ok && n < p.N) {
-        if (n + 16 <= p.N) {
+    const int quarter = warp & 3;                    // TMEM lanes 32·quarter .. +31 are accessible to this warp
+    long long tc = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
+      const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
+      const int acc = (int)(tc & 1);
+      const int row = m0 + quarter * 32 + lane;
+      mbar_wait(&acc_full[acc], (uint32_t)((tc >> 1) & 1));
+      tc_fence_after();
+      const bool row_ok = row < p.M;
+      float *crow = p.C + (long long)row * p.ldc;
+      const float *rrow = p.residual ? p.residual + (long long)row * p.ldr : nullptr;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols);
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);          // warp-wide: executed by all lanes
+        const int n = n0 + c0;
+        if (row_ok && n < p.N) {
+          if (n + 16 <= p.N) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (p.bias) {
-              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + q);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            for (int q = 0; q < 4; ++q) {
+              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              if (p.bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + q);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (rrow) {
+                const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow + n) + q);
+                if (p.rscale) {
+                  const float4 s = __ldg(reinterpret_cast<const float4 *>(p.rscale + n) + q);
+                  o.x = fmaf(r.x, s.x, o.x); o.y = fmaf(r.y, s.y, o.y); o.z = fmaf(r.z, s.z, o.z); o.w = fmaf(r.w, s.w, o.w);
+                } else {
+                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                }
+              }
+              reinterpret_cast<float4 *>(crow + n)[q] = o;
             }
-            if (rrow) {
-              const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow + n) + q);
-              if (p.rscale) {
-                const float4 s = __ldg(reinterpret_cast<const float4 *>(p.rscale + n) + q);
-                o.x = fmaf(r.x, s.x, o.x); o.y = fmaf(r.y, s.y, o.y); o.z = fmaf(r.z, s.z, o.z); o.w = fmaf(r.w, s.w, o.w);
-              } else {
-                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              if (n + i < p.N) {
+                float o = v[i];
+                if (p.bias) o += p.bias[n + i];
+                if (rrow) o = p.rscale ? fmaf(rrow[n + i], p.rscale[n + i], o) : o + rrow[n + i];
+                crow[n + i] = o;
               }
             }
-            reinterpret_cast<float4 *>(crow + n)[q] = o;
-          }
-        } else {
-          for (int i = 0; i < 16 && n + i < p.N; ++i) {
-            float o = v[i];
-            if (p.bias) o += p.bias[n + i];
-            if (rrow) o = p.rscale ? fmaf(rrow[n + i], p.rscale[n + i], o) : o + rrow[n + i];
-            crow[n + i] = o;
           }
         }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);    // this warp no longer reads the accumulator stage
     }
   }
   tc_fence_before();
@@ -232,17 +263,20 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   p.bias = bias; p.residual = residual; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
   p.M = (int)M; p.N = N; p.K = K;
   p.BN = pick_bn(N);
-  p.tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  p.tmem_cols = 2 * (p.BN <= 16 ? 16 : p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256);   // two accumulator stages
+  if (p.tmem_cols < 32) p.tmem_cols = 32;
   int rc;
   if ((rc = make_tmap_2d_sw128(&p.m_a, A, M, K, lda, GM_BM))) return rc;
   if ((rc = make_tmap_2d_sw128(&p.m_w, W, N, K, K, p.BN))) return rc;
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int nkb = (K + GM_BK - 1) / GM_BK;
-  p.stages = std::max(2, std::min(std::min(6, nkb), (100 * 1024) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16;
+  p.stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((N + p.BN - 1) / p.BN, (unsigned)((M + GM_BM - 1) / GM_BM));
+  const long long total = (long long)((N + p.BN - 1) / p.BN) * ((M + GM_BM - 1) / GM_BM);
+  const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
+  const unsigned grid = (unsigned)std::min<long long>(total, 148LL * ctas_per_sm);   // persistent CTAs
   gemm_tf32_kernel<<<grid, 192, smem, stream>>>(p);
   SIGMA_CHECK_LAUNCH();
   return SIGMA_OK;
