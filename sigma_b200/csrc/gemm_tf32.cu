@@ -23,7 +23,7 @@ constexpr int GM_BK = 32;    // fp32 elements per k-block = one 128-byte swizzle
 constexpr int GM_UK = 8;     // UMMA_K for kind::tf32 (32 bytes)
 
 struct alignas(64) GemmParams {
-  CUtensorMap m_a, m_w;
+  CUtensorMap m_a, m_w, m_c;
   const float *bias, *residual, *rscale;
   float *C;
   long long ldr, ldc;
@@ -82,6 +82,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+        "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+        "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void *smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"((uint64_t)map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int BN = p.BN, S = p.stages;
@@ -103,6 +123,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.m_a);
     tma_prefetch_desc(&p.m_w);
+    tma_prefetch_desc(&p.m_c);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     fence_mbar_init();
@@ -161,8 +182,14 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       }
     }
   } else {
-    // ===== epilogue warps: TMEM -> registers -> (+bias, +residual·rscale) -> global =====
+    // ===== epilogue warps: TMEM -> registers -> (+bias, +residual·rscale) -> swizzled smem -> TMA store =====
+    // Each warp owns 32 rows (its TMEM lane quarter) and moves them out in chunks of 32 columns: one thread = one
+    // row, its 32 values go to a 128-byte shared row (16-byte chunks XOR-swizzled by row & 7, the layout the
+    // SWIZZLE_128B tensor map expects), then ONE TMA store writes the 32 x 32 box as 128-byte rows.  TMA clips the
+    // box at M and N, so ragged tiles need no masks.  Two staging buffers per warp.
     const int quarter = warp & 3;                    // TMEM lanes 32·quarter .. +31 are accessible to this warp
+    unsigned char *stage_c = smem_raw + (size_t)S * stage_bytes + 1024 + (size_t)quarter * 2 * 4096;
+    int buf = 0;
     long long tc = 0;
     for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
       const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
@@ -171,50 +198,50 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       mbar_wait(&acc_full[acc], (uint32_t)((tc >> 1) & 1));
       tc_fence_after();
       const bool row_ok = row < p.M;
-      float *crow = p.C + (long long)row * p.ldc;
-      const float *rrow = p.residual ? p.residual + (long long)row * p.ldr : nullptr;
+      const float *rrow = (p.residual && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols);
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);          // warp-wide: executed by all lanes
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         const int n = n0 + c0;
-        if (row_ok && n < p.N) {
-          if (n + 16 <= p.N) {
+        if (n >= p.N) break;                          // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c0, v);          // warp-wide
+        float4 *dst = reinterpret_cast<float4 *>(stage_c + buf * 4096 + lane * 128);
+        if (lane == 0) tma_store_wait_read<1>();     // the store that last used this buffer has finished reading it
+        __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-              if (p.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + n) + q);
-                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-              }
-              if (rrow) {
-                const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow + n) + q);
-                if (p.rscale) {
-                  const float4 s = __ldg(reinterpret_cast<const float4 *>(p.rscale + n) + q);
-                  o.x = fmaf(r.x, s.x, o.x); o.y = fmaf(r.y, s.y, o.y); o.z = fmaf(r.z, s.z, o.z); o.w = fmaf(r.w, s.w, o.w);
-                } else {
-                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
-              }
-              reinterpret_cast<float4 *>(crow + n)[q] = o;
+        for (int q = 0; q < 8; ++q) {
+          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          const int nn = n + 4 * q;
+          if (nn < p.N) {                             // N % 4 == 0, so a float4 is all-in or all-out
+            if (p.bias) {
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + nn));
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (n + i < p.N) {
-                float o = v[i];
-                if (p.bias) o += p.bias[n + i];
-                if (rrow) o = p.rscale ? fmaf(rrow[n + i], p.rscale[n + i], o) : o + rrow[n + i];
-                crow[n + i] = o;
+            if (rrow) {
+              const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow + nn));
+              if (p.rscale) {
+                const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.rscale + nn));
+                o.x = fmaf(r.x, sc.x, o.x); o.y = fmaf(r.y, sc.y, o.y); o.z = fmaf(r.z, sc.z, o.z); o.w = fmaf(r.w, sc.w, o.w);
+              } else {
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
               }
             }
           }
+          dst[q ^ (lane & 7)] = o;
         }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.m_c, stage_c + buf * 4096, n, m0 + quarter * 32);
+          tma_store_commit();
+        }
+        buf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);    // this warp no longer reads the accumulator stage
     }
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -248,11 +275,31 @@ static int make_tmap_2d_sw128(CUtensorMap *map, const float *base, long long row
   return SIGMA_OK;
 }
 
+// BN is a multiple of 32 (the epilogue moves 32-column boxes); tiles that overhang N are clipped by TMA on both the
+// W load (zero fill) and the C store.
 static int pick_bn(int N) {
-  if (N <= 256 && N % 16 == 0) return N;
-  for (int bn = 256; bn >= 64; bn -= 16)
+  if (N <= 256) return ((N + 31) / 32) * 32;
+  for (int bn = 256; bn >= 128; bn -= 32)
     if (N % bn == 0) return bn;
-  return 128;  // ragged N: the last tile is masked (TMA zero-fills the missing rows of W)
+  return 256;
+}
+
+static int make_tmap_c(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld) {
+  EncodeTiledFn2 fn = (EncodeTiledFn2)get_tensor_map_encoder();
+  if (!fn) return SIGMA_ECUDA;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t bdim[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstr, bdim, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (gemm output) failed (CUresult %d): rows=%lld cols=%lld ld=%lld base=%p", (int)r, rows,
+              cols, ld, (const void *)base);
+    return SIGMA_ECUDA;
+  }
+  return SIGMA_OK;
 }
 
 int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *bias, const float *residual, long long ldr,
@@ -268,11 +315,12 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   int rc;
   if ((rc = make_tmap_2d_sw128(&p.m_a, A, M, K, lda, GM_BM))) return rc;
   if ((rc = make_tmap_2d_sw128(&p.m_w, W, N, K, K, p.BN))) return rc;
+  if ((rc = make_tmap_c(&p.m_c, C, M, N, ldc))) return rc;
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int nkb = (K + GM_BK - 1) / GM_BK;
-  p.stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16;
+  p.stages = std::max(2, std::min(6, (128 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 4 * 2 * 4096 /*epilogue staging*/;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)((N + p.BN - 1) / p.BN) * ((M + GM_BM - 1) / GM_BM);
   const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
