@@ -6,8 +6,8 @@
 // 5th-generation tensor cores: `tcgen05.mma.cta_group::1.kind::tf32` issued by one elected thread, fp32 operands
 // read as TF32 straight from shared memory (no conversion pass), fp32 accumulators in TMEM, operand tiles staged
 // by TMA (128-byte swizzle) through a full/empty mbarrier ring, accumulators read back with `tcgen05.ld` and the
-// bias / residual epilogue fused before the store.  Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM
-// allocator + MMA issuer, warps 2-5 = epilogue (each owns the TMEM lane quarter `warp % 4`).
+// bias / residual epilogue fused before the store.  Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer, warps 2-9 = epilogue (two per TMEM lane quarter `warp % 4`, alternating column chunks).
 // Persistent CTAs loop over 128 x BN output tiles (BN <= 256, multiple of 16, a runtime value chosen per call) with
 // two TMEM accumulator stages, so the loads and MMAs of the next tile overlap the epilogue of the current one.
 // These GEMMs are HBM-bound at the Sigma shapes (K = 96..1536): what matters is one pass over A and one over C.
@@ -102,7 +102,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                : "memory");
 }
 
-__global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int BN = p.BN, S = p.stages;
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = BN * GM_BK * 4;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
     tma_prefetch_desc(&p.m_w);
     tma_prefetch_desc(&p.m_c);
     for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_mbar_init();
   }
   if (warp == 1) {  // TMEM allocation is a warp-wide operation; the same warp frees it
@@ -188,7 +188,8 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
     // SWIZZLE_128B tensor map expects), then ONE TMA store writes the 32 x 32 box as 128-byte rows.  TMA clips the
     // box at M and N, so ragged tiles need no masks.  Two staging buffers per warp.
     const int quarter = warp & 3;                    // TMEM lanes 32·quarter .. +31 are accessible to this warp
-    unsigned char *stage_c = smem_raw + (size_t)S * stage_bytes + 1024 + (size_t)quarter * 2 * 4096;
+    const int chalf = (warp - 2) >> 2;               // two warps per lane quarter: even / odd 32-column chunks
+    unsigned char *stage_c = smem_raw + (size_t)S * stage_bytes + 1024 + (size_t)(warp - 2) * 2 * 4096;
     int buf = 0;
     long long tc = 0;
     for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(192) gemm_tf32_kernel(const __grid_constant__ 
       const bool row_ok = row < p.M;
       const float *rrow = (p.residual && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 32 * chalf; c0 < BN; c0 += 64) {
         const int n = n0 + c0;
         if (n >= p.N) break;                          // warp-uniform
         float v[32];
@@ -319,13 +320,13 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int nkb = (K + GM_BK - 1) / GM_BK;
-  p.stages = std::max(2, std::min(6, (128 * 1024) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 4 * 2 * 4096 /*epilogue staging*/;
+  p.stages = std::max(2, std::min(6, (120 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 8 * 2 * 4096 /*epilogue staging*/;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)((N + p.BN - 1) / p.BN) * ((M + GM_BM - 1) / GM_BM);
   const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
   const unsigned grid = (unsigned)std::min<long long>(total, 148LL * ctas_per_sm);   // persistent CTAs
-  gemm_tf32_kernel<<<grid, 192, smem, stream>>>(p);
+  gemm_tf32_kernel<<<grid, 320, smem, stream>>>(p);
   SIGMA_CHECK_LAUNCH();
   return SIGMA_OK;
 }
