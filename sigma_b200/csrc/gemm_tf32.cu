@@ -186,11 +186,11 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
     // Each warp owns 32 rows (its TMEM lane quarter) and moves them out in chunks of 32 columns: one thread = one
     // row, its 32 values go to a 128-byte shared row (16-byte chunks XOR-swizzled by row & 7, the layout the
     // SWIZZLE_128B tensor map expects), then ONE TMA store writes the 32 x 32 box as 128-byte rows.  TMA clips the
-    // box at M and N, so ragged tiles need no masks.  Two staging buffers per warp.
+    // box at M and N, so ragged tiles need no masks.  One 4 KB staging buffer per warp (the tcgen05.ld of the next
+    // chunk overlaps the previous store), which leaves room for a 4-deep operand ring at BN = 256.
     const int quarter = warp & 3;                    // TMEM lanes 32·quarter .. +31 are accessible to this warp
     const int chalf = (warp - 2) >> 2;               // two warps per lane quarter: even / odd 32-column chunks
-    unsigned char *stage_c = smem_raw + (size_t)S * stage_bytes + 1024 + (size_t)(warp - 2) * 2 * 4096;
-    int buf = 0;
+    unsigned char *stage_c = smem_raw + (size_t)S * stage_bytes + 1024 + (size_t)(warp - 2) * 4096;
     long long tc = 0;
     for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++tc) {
       const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
@@ -206,8 +206,8 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
         if (n >= p.N) break;                          // warp-uniform
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);          // warp-wide
-        float4 *dst = reinterpret_cast<float4 *>(stage_c + buf * 4096 + lane * 128);
-        if (lane == 0) tma_store_wait_read<1>();     // the store that last used this buffer has finished reading it
+        float4 *dst = reinterpret_cast<float4 *>(stage_c + lane * 128);
+        if (lane == 0) tma_store_wait_read<0>();     // the previous store of this warp has finished reading the buffer
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -233,10 +233,9 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&p.m_c, stage_c + buf * 4096, n, m0 + quarter * 32);
+          tma_store_2d(&p.m_c, stage_c, n, m0 + quarter * 32);
           tma_store_commit();
         }
-        buf ^= 1;
       }
       tc_fence_before();
       __syncwarp();
@@ -320,8 +319,8 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
   const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
   const int nkb = (K + GM_BK - 1) / GM_BK;
-  p.stages = std::max(2, std::min(6, (120 * 1024) / stage_bytes));
-  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 8 * 2 * 4096 /*epilogue staging*/;
+  p.stages = std::max(2, std::min(8, (192 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)((N + p.BN - 1) / p.BN) * ((M + GM_BM - 1) / GM_BM);
   const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
