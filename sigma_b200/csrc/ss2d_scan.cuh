@@ -182,7 +182,7 @@ __device__ __forceinline__ void scan_tile(Ss2dThread<N, CPT, RP> &t, const float
 }
 
 template <int N, int CPT, int RP, int MODE>
-__global__ void __launch_bounds__(160, (N >= 16 ? 1 : 4)) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+__global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
 
