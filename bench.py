@@ -31,9 +31,9 @@ import torch  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=32, help="images per GPU per step")
     ap.add_argument("--impl", default="sigma", choices=["sigma", "reference"])
     ap.add_argument("--model", default="sigma_tiny")
     ap.add_argument("--height", type=int, default=480)

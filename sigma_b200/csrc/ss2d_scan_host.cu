@@ -148,14 +148,18 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
       return rc;
     max_tiles = std::max(max_tiles, p.O[k] * ((p.I[k] + LT - 1) / LT));
   }
-  // L-segments: only when the unsplit grid cannot give every SM sub-partition (148 x 4) work.  Each split
-  // repeats the exponentials (MODE_SUMMARY), which is what bounds the d_state=16 scans, so those are split
-  // only up to one warp per sub-partition; the d_state<=8 scans (HBM-bound) up to two.
+  // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY): a second pass over the data, so only when the unsplit grid
+  // leaves SM sub-partitions (148 x 4) without a warp.  Measured on B200 (profiles/r01_scan_variants.txt): with >= 1
+  // warp per sub-partition a single pass wins; below that, d_state <= 8 scans are best split "big" (to ~2 warps per
+  // sub-partition), d_state = 16 scans (each split repeats 16 exponentials per element) only up to ~1.
   const long long ctas = (long long)((D + DT - 1) / DT) * ndir * batch;
   const long long warps = ctas * NW;
-  const long long want = 148LL * 4 * (N >= 16 ? 1 : 2);
+  const long long full = 148LL * 4;
   int nsplit = 1;
-  if (warps < want) nsplit = (int)std::min<long long>((want + warps - 1) / warps, kMaxSplit);
+  if (warps < full) {
+    const long long want = N >= 16 ? full : 2 * full;
+    nsplit = (int)std::min<long long>((want + warps - 1) / warps, kMaxSplit);
+  }
   if (force_split > 0) nsplit = std::min(force_split, kMaxSplit);
   if (ws == nullptr || ws_bytes < ss2d_scan_workspace_bytes(kind, batch, D, N)) {
     if (force_split > 1) { set_error("sigma_ss2d_scan_fwd: workspace too small for %d segments", force_split); return SIGMA_EWORKSPACE; }
