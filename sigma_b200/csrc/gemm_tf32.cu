@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
         const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = (int)(it % S);
-          mbar_wait(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));
+          mbar_wait_backoff(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));
           unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
           mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + b_bytes));
           tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);

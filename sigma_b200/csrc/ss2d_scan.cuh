@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const
       for (int tau = t0; tau < t1; ++tau) {
         const int it = tau - t0, st = it % NST;
         if ((p.ablate & 4) && it >= NST) break;
-        mbar_wait(&empty[st], (uint32_t)(((it / NST) & 1) ^ 1));   // fresh barrier: parity 1 passes immediately
+        mbar_wait_backoff(&empty[st], (uint32_t)(((it / NST) & 1) ^ 1));   // fresh barrier: parity 1 passes immediately
         float *dst = stages + st * stage_fl;
         int o, i0;
         tile_coord(tau, o, i0);
