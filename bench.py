@@ -221,6 +221,9 @@ def measure_roofline(model, rgb, mx, reps=3):
         s_[0] += b
         s_[1] += ms
         s_[2] += 1
+        if os.environ.get("SIGMA_BENCH_DETAIL"):
+            print(f"[scan call] kind={c[0]} batch={c[7]} HxW={c[8]}x{c[9]} D={c[10]} N={c[11]} R={c[12]}: {ms:.3f} ms "
+                  f"{b / ms / 1e6:.0f} GB/s", file=sys.stderr)
     return tot_b, tot_ms, len(calls), 1, by_n
 
 

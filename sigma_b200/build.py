@@ -26,7 +26,7 @@ def _sources():
 
 
 def _headers_mtime():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     hs.append(os.path.join(os.path.dirname(ROOT), "include", "sigma_b200.h"))
     return max(os.path.getmtime(h) for h in hs)
 

@@ -15,10 +15,15 @@
 // History (profiles/r01_scan_variants.txt): 4 lanes/channel was issue-bound; 1 thread/channel with scalar
 // fp32 left MUFU, the LDS return path (2N floats of B/C per channel-position) and issue each ~50 % busy;
 // CPT = 2 halves the B/C traffic per channel and FFMA2 halves the fp32 issue slots.
-// CTA = (channel tile DT, direction k [x L-segment], image b) = DT/32 consumer warps + one TMA producer warp.
+// CTA = (channel tile DT, direction k [x L-segment], image b) = DT/32 warps, all computing.
 // Tiles of LT scan positions are staged HBM -> shared by TMA (cp.async.bulk.tensor) through an NST-deep ring
-// guarded by full/empty mbarriers, so consumer warps never wait for each other (no CTA-wide barrier in the
-// loop); y goes straight from registers to HBM (a warp writes 32 consecutive channels of one position = one
+// (no CTA-wide barrier in the loop): a "full" mbarrier per slot signals TMA completion; a per-slot arrival counter
+// replaces the usual "empty" barrier — the warp whose arrival completes a round (the LAST warp to finish the tile)
+// immediately requests the tile that reuses the slot, so nobody ever waits for a slot and a tile is requested
+// NST-1 tiles ahead of its first use.  An earlier version had a dedicated producer warp; it cost a fifth of the
+// register file (12 instead of 16 scanning warps per SM at 128 registers).  Waits on "full" are non-suspending
+// spins (test_wait): a suspended try_wait costs a microsecond-scale wake-up.
+// y goes straight from registers to HBM (a warp writes 32 consecutive channels of one position = one
 // 128-byte row).
 // Per group of 4 positions the delta' of the NEXT group is computed while the recurrence of the current one
 // runs (software pipelining: the only serial dependency is the fma h = a·h + b).
@@ -30,8 +35,11 @@ namespace sigma {
 
 template <int N>
 struct Ss2dCfg {
-  static constexpr int LT = N >= 16 ? 16 : 32;   // scan positions per tile
-  static constexpr int NST = N >= 16 ? 4 : 3;    // TMA ring depth
+  static constexpr int G = N >= 16 ? 4 : 8;       // positions per software-pipelined group (measured: 8/16 lose at N=16, 16 loses at N=4)
+  static constexpr int LT = N >= 16 ? 16 : 32;    // scan positions per tile (multiple of G)
+  static constexpr int NST = N >= 16 ? 4 : 3;     // TMA ring depth
+  static constexpr int MAXW = 4;                  // warps per CTA
+  static constexpr int CTAS = 3;                  // resident CTAs per SM the register budget is set for (168 regs)
 };
 
 struct alignas(64) Ss2dParams {
@@ -43,75 +51,107 @@ struct alignas(64) Ss2dParams {
   int I[4], O[4], rev[4];
   long long istride[4], ostride[4];   // y element strides of the inner / outer walk index
   int nsplit, tiles_per_split;
-  int ablate;  // timing experiments only (SIGMA_SCAN_ABLATE): 1 = no y store, 2 = no per-group prologue, 4 = no TMA reload
+  int ablate;  // timing experiments, only in builds with -DSIGMA_SCAN_ABLATION (SIGMA_SCAN_ABLATE env):
+               // 1 = no y store, 2 = no per-group prologue, 4 = no TMA reload
 };
+
+#ifdef SIGMA_SCAN_ABLATION
+#define SIGMA_ABL(flags, m) (((flags) & (m)) != 0)
+#else
+#define SIGMA_ABL(flags, m) false
+#endif
 
 __host__ __device__ inline size_t ss2d_smem_bytes(int LT, int DT, int NST, int Cp, bool cross) {
   const size_t stage = (size_t)LT * DT + (size_t)LT * Cp * (cross ? 2 : 1);
-  return NST * stage * sizeof(float) + 128 /*barriers*/;
+  return NST * stage * sizeof(float) + 128 /*barriers + counters*/;
 }
 
 template <int N, int CPT, int RP>
 struct Ss2dThread {
   float h[CPT][N], a2[CPT][N], W[CPT][RP];
-  float bias[CPT], Dv[CPT], sumdl[CPT];
-  int ch;          // first channel of this thread inside the CTA tile; the c-th is ch + c*DT/CPT
-  int ablate;
+  unsigned long long bias2[CPT];   // {dt bias, 0} as one 64-bit register pair: initial value of the dt_proj accumulator
+  float Dv[CPT], sumdl[CPT];
   bool ok[CPT];
+  int ablate;
 };
 
-// delta' and u of both channels for the 4 positions of group j (tile rows 4j..4j+3).  dt_r is read once per
-// position (broadcast LDS.128) and used for all CPT channels; the dot products run on FFMA2 pairs.
-template <int N, int CPT, int RP>
-__device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, const float *sXC, const float *sDB, int DT,
-                                               int j, float (&dl)[CPT][4], float (&u)[CPT][4]) {
+// packed helpers on raw 64-bit register pairs (keep loop-invariant pairs paired: no MOVs to rebuild them)
+__device__ __forceinline__ unsigned long long fma2_raw(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+__device__ __forceinline__ unsigned long long mul2_raw(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
+// delta' and u of the thread's channels for the G positions whose x_dbl rows start at `drow` (pointing at the
+// dt_r part of the first row) and whose xc values start at `xrow` (this thread's first channel).  dt_r is read
+// once per position (broadcast LDS.128) and used for all CPT channels; the dot product runs on FFMA2 pairs
+// (one accumulator chain up to RP = 12, two beyond), softplus is branch-free (common.cuh).
+template <int N, int CPT, int RP, int G>
+__device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, const float *xrow, const float *drow, int DT,
+                                               float (&dl)[CPT][G], float (&u)[CPT][G]) {
   constexpr int Cp = 2 * N + RP;  // x_dbl row length: [B | C | dt_r padded to RP] (sigma_ss2d_padded_cp)
+  constexpr bool TWO = RP >= 16;
   const int cstride = DT / CPT;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float *row = sDB + (4 * j + e) * Cp + 2 * N;
-    f2 acc[CPT][2];
+  for (int e = 0; e < G; ++e) {
+    const float *row = drow + e * Cp;
+    unsigned long long acc0[CPT], acc1[CPT];
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) { acc[c][0] = f2{t.bias[c], 0.f}; acc[c][1] = f2{0.f, 0.f}; }
+    for (int c = 0; c < CPT; ++c) { acc0[c] = t.bias2[c]; acc1[c] = 0ull; }
 #pragma unroll
     for (int q4 = 0; q4 < RP / 4; ++q4) {
       const float4 v = *reinterpret_cast<const float4 *>(row + 4 * q4);   // broadcast read, shared by CPT channels
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
-        acc[c][0] = fma2(f2{t.W[c][4 * q4 + 0], t.W[c][4 * q4 + 1]}, f2{v.x, v.y}, acc[c][0]);
-        acc[c][1] = fma2(f2{t.W[c][4 * q4 + 2], t.W[c][4 * q4 + 3]}, f2{v.z, v.w}, acc[c][1]);
+        acc0[c] = fma2_raw(pack2(t.W[c][4 * q4 + 0], t.W[c][4 * q4 + 1]), pack2(v.x, v.y), acc0[c]);
+        if (TWO) {
+          acc1[c] = q4 == 0 ? mul2_raw(pack2(t.W[c][2], t.W[c][3]), pack2(v.z, v.w))
+                            : fma2_raw(pack2(t.W[c][4 * q4 + 2], t.W[c][4 * q4 + 3]), pack2(v.z, v.w), acc1[c]);
+        } else {
+          acc0[c] = fma2_raw(pack2(t.W[c][4 * q4 + 2], t.W[c][4 * q4 + 3]), pack2(v.z, v.w), acc0[c]);
+        }
       }
     }
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-      dl[c][e] = softplus20((acc[c][0].x + acc[c][0].y) + (acc[c][1].x + acc[c][1].y));
-      u[c][e] = sXC[(4 * j + e) * DT + t.ch + c * cstride];
+      const f2 s0 = unpack2(acc0[c]);
+      float x = s0.x + s0.y;
+      if (TWO) { const f2 s1 = unpack2(acc1[c]); x += s1.x + s1.y; }
+      dl[c][e] = softplus20(x);
+      u[c][e] = xrow[e * DT + c * cstride];
     }
   }
 }
 
-// recurrence over `cnt` (<= 4) positions of group j, in walk order (REV: descending tile rows).
+// recurrence over `cnt` (<= G) positions of one group, in walk order (REV: descending tile rows).  `rb` = first
+// x_dbl row of the group (B part), `rc` = same row in the tile C is read from, `yp` = y of the group's first
+// position (this thread's first channel), `ystride` = y elements between consecutive positions.
 // Per position B and C are read ONCE (2·N/4 broadcast LDS.128) and reused by the CPT channels of the thread;
 // per channel and state pair: FMUL2 (exp arguments), 2 x MUFU.EX2, FMUL2 (delta·u·B), FFMA2 (h), FFMA2 (C·h).
-template <int N, int CPT, int RP, bool WITH_Y, bool REV, bool FULL>
-__device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *sDB, const float *sDC, float *yrow,
-                                           long long ystride, int ycstride, int j, const float (&dl)[CPT][4],
-                                           const float (&u)[CPT][4], int cnt) {
+template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL>
+__device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *rb, const float *rc, float *yp,
+                                           long long ystride, int ycstride, const float (&dl)[CPT][G],
+                                           const float (&u)[CPT][G], int cnt) {
   constexpr int Cp = 2 * N + RP;
+  constexpr int NCH = N >= 8 ? 2 : 1;   // independent C·h accumulator chains per channel
 #pragma unroll
-  for (int ii = 0; ii < 4; ++ii) {
-    const int i = REV ? 3 - ii : ii;
+  for (int ii = 0; ii < G; ++ii) {
+    const int i = REV ? G - 1 - ii : ii;
     if (FULL || i < cnt) {
-      const float *rb = sDB + (4 * j + i) * Cp;
-      const float *rc = sDC + (4 * j + i) * Cp + N;
-      f2 yacc[CPT][2];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) yacc[c][0] = yacc[c][1] = f2{0.f, 0.f};
+      const float *pb = rb + i * Cp;
+      const float *pc = rc + i * Cp;
+      f2 yacc[CPT][NCH];
 #pragma unroll
       for (int s4 = 0; s4 < N / 4; ++s4) {
-        const float4 bv = *reinterpret_cast<const float4 *>(rb + 4 * s4);   // broadcast reads
+        const float4 bv = *reinterpret_cast<const float4 *>(pb + 4 * s4);   // broadcast reads
         float4 cv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (WITH_Y) cv = *reinterpret_cast<const float4 *>(rc + 4 * s4);
+        if (WITH_Y) cv = *reinterpret_cast<const float4 *>(pc + 4 * s4);
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
           const float d = dl[c][i], du = dl[c][i] * u[c][i];
@@ -123,16 +163,22 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
             const f2 bb = mul2(f2{du, du}, hp == 0 ? f2{bv.x, bv.y} : f2{bv.z, bv.w});
             const f2 hn = fma2(a, f2{t.h[c][s], t.h[c][s + 1]}, bb);
             t.h[c][s] = hn.x; t.h[c][s + 1] = hn.y;
-            if (WITH_Y) yacc[c][hp] = fma2(hn, hp == 0 ? f2{cv.x, cv.y} : f2{cv.z, cv.w}, yacc[c][hp]);
+            if (WITH_Y) {
+              const f2 cc = hp == 0 ? f2{cv.x, cv.y} : f2{cv.z, cv.w};
+              const int ch = NCH == 2 ? hp : 0;
+              const bool first = NCH == 2 ? s4 == 0 : (s4 == 0 && hp == 0);
+              yacc[c][ch] = first ? mul2(hn, cc) : fma2(hn, cc, yacc[c][ch]);
+            }
           }
         }
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
         if (WITH_Y) {
-          const float y = (yacc[c][0].x + yacc[c][0].y) + (yacc[c][1].x + yacc[c][1].y);
-          if (t.ok[c] && !(t.ablate & 1)) yrow[(long long)(4 * j + i) * ystride + c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
-          if (t.ablate & 1) t.sumdl[c] += y;
+          float y = yacc[c][0].x + yacc[c][0].y;
+          if (NCH == 2) y += yacc[c][1].x + yacc[c][1].y;
+          if (SIGMA_ABL(t.ablate, 1)) t.sumdl[c] += y;
+          else if (t.ok[c]) yp[(long long)i * ystride + c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
         } else {
           t.sumdl[c] += dl[c][i];
         }
@@ -141,48 +187,109 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
   }
 }
 
-template <int N, int CPT, int RP, bool WITH_Y, bool REV>
-__device__ __forceinline__ void scan_tile(Ss2dThread<N, CPT, RP> &t, const float *sXC, const float *sDB, const float *sDC,
-                                          float *yrow, long long ystride, int DT, int npos) {
-  const int nfull = npos >> 2, rem = npos & 3;
-  const int ycs = DT / CPT;
-  float dl[CPT][4], u[CPT][4];
-  if (REV && rem) {  // the ragged group comes first when walking backwards
-    group_prologue<N, CPT, RP>(t, sXC, sDB, DT, nfull, dl, u);
-    group_body<N, CPT, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, ycs, nfull, dl, u, rem);
-  }
-  if (nfull > 0) {
-    int j = REV ? nfull - 1 : 0;
-    group_prologue<N, CPT, RP>(t, sXC, sDB, DT, j, dl, u);
+// Everything a warp needs to walk its CTA's tiles; filled once in the kernel.
+template <int N, int CPT, int RP>
+struct Ss2dWalk {
+  float *stages;
+  uint64_t *full;
+  uint32_t *done;
+  float *ybase;
+  long long istride, ostride;
+  int stage_fl, xc_fl, dbl_fl, DT, nwarps, lane, ch;
+  int t0, t1, TPO, ntiles, I;
+  bool cross, rev;
+};
+
+// The tile loop of one warp.  The software pipeline over groups of G positions runs ACROSS tiles: while the
+// recurrence of group g runs, delta'/u of group g+1 are computed — from the next tile's ring slot when g is the
+// last group of its tile — so no prologue is exposed at a tile boundary and none is computed twice.
+template <int N, int CPT, int RP, bool WITH_Y, bool REV, typename Request>
+__device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2dWalk<N, CPT, RP> &w, Request &&request_tile) {
+  constexpr int G = Ss2dCfg<N>::G, LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
+  constexpr int Cp = 2 * N + RP;
+  const int ycs = w.DT / CPT;
+
+  struct Tile { const float *sXC, *sDB, *sDC; float *yrow; int npos, ng; };
+  auto open_tile = [&](int tau) {   // waits for the tile's TMA bytes; returns its pointers
+    const int it = tau - w.t0, st = it % NST;
+    if (!(SIGMA_ABL(t.ablate, 4) && it >= NST)) mbar_spin(&w.full[st], (uint32_t)((it / NST) & 1));
+    Tile T;
+    T.sXC = w.stages + st * w.stage_fl;
+    T.sDB = T.sXC + w.xc_fl;
+    T.sDC = w.cross ? T.sDB + w.dbl_fl : T.sDB;
+    const int tm = w.rev ? w.ntiles - 1 - tau : tau;
+    const int o = tm / w.TPO, i0 = (tm - o * w.TPO) * LT;
+    T.npos = min(LT, w.I - i0);
+    T.ng = (T.npos + G - 1) / G;
+    T.yrow = w.ybase + (long long)o * w.ostride + (long long)i0 * w.istride;
+    return T;
+  };
+
+  if (w.t0 >= w.t1) return;
+  Tile cur = open_tile(w.t0);
+  int j = REV ? cur.ng - 1 : 0;   // walking backwards, a ragged group (npos % G) comes first
+  float dl[CPT][G], u[CPT][G];
+  group_prologue<N, CPT, RP, G>(t, cur.sXC + j * G * w.DT + w.ch, cur.sDB + j * G * Cp + 2 * N, w.DT, dl, u);
+
+  for (int tau = w.t0; tau < w.t1; ++tau) {
+    Tile nxt = cur;
+    int jn = j;
 #pragma unroll 1
-    for (int g = 0; g < nfull; ++g) {
-      // next group's delta'/u first (clamped index: the last iteration recomputes a valid group, unused),
-      // so its loads / dot products / softplus overlap this group's exponentials and fma chains
-      const int jn = REV ? max(j - 1, 0) : min(j + 1, nfull - 1);
-      float dln[CPT][4], un[CPT][4];
-      if (!(t.ablate & 2)) group_prologue<N, CPT, RP>(t, sXC, sDB, DT, jn, dln, un);
-      else {
-#pragma unroll
-        for (int c = 0; c < CPT; ++c)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
+    for (int g = 0; g < cur.ng; ++g) {
+      // next group's delta'/u first, so its loads / dot products / softplus overlap this group's exponentials
+      const float *px, *pd;
+      if (g + 1 < cur.ng) {
+        jn = REV ? j - 1 : j + 1;
+        px = cur.sXC + jn * G * w.DT + w.ch;
+        pd = cur.sDB + jn * G * Cp + 2 * N;
+      } else if (tau + 1 < w.t1) {
+        nxt = open_tile(tau + 1);
+        jn = REV ? nxt.ng - 1 : 0;
+        px = nxt.sXC + jn * G * w.DT + w.ch;
+        pd = nxt.sDB + jn * G * Cp + 2 * N;
+      } else {                       // very last group of the walk: recompute the current one (result unused)
+        px = cur.sXC + j * G * w.DT + w.ch;
+        pd = cur.sDB + j * G * Cp + 2 * N;
       }
-      group_body<N, CPT, RP, WITH_Y, REV, true>(t, sDB, sDC, yrow, ystride, ycs, j, dl, u, 4);
+      float dln[CPT][G], un[CPT][G];
+      const int cnt = cur.npos - j * G;
+      const float *rb = cur.sDB + j * G * Cp;
+      const float *rc = cur.sDC + j * G * Cp + N;
+      float *yp = cur.yrow + (long long)(j * G) * w.istride;
+      // prologue(next) and body(current) are independent; keeping them in ONE basic block lets ptxas interleave
+      // the prologue's FMA/LG2 work with the body's exponentials (it does not schedule across the cnt branch)
+      if (cnt >= G) {
+        if (!SIGMA_ABL(t.ablate, 2)) group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
+        else {
+#pragma unroll
+          for (int c = 0; c < CPT; ++c)
+#pragma unroll
+            for (int i = 0; i < G; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
+        }
+        group_body<N, CPT, RP, G, WITH_Y, REV, true>(t, rb, rc, yp, w.istride, ycs, dl, u, G);
+      } else {
+        group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
+        group_body<N, CPT, RP, G, WITH_Y, REV, false>(t, rb, rc, yp, w.istride, ycs, dl, u, cnt);
+      }
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) { dl[c][i] = dln[c][i]; u[c][i] = un[c][i]; }
-      j = REV ? j - 1 : j + 1;
+        for (int i = 0; i < G; ++i) { dl[c][i] = dln[c][i]; u[c][i] = un[c][i]; }
+      j = jn;
     }
-  }
-  if (!REV && rem) {
-    group_prologue<N, CPT, RP>(t, sXC, sDB, DT, nfull, dl, u);
-    group_body<N, CPT, RP, WITH_Y, REV, false>(t, sDB, sDC, yrow, ystride, ycs, nfull, dl, u, rem);
+    // this warp is done with the ring slot; the last of the CTA's warps to get here refills it
+    __syncwarp();
+    if (w.lane == 0 && tau + NST < w.t1) {
+      const int st = (tau - w.t0) % NST;
+      const uint32_t old = smem_inc_acq_rel(&w.done[st]);
+      if ((old + 1) % (uint32_t)w.nwarps == 0) request_tile(tau + NST);
+    }
+    cur = nxt;
   }
 }
 
 template <int N, int CPT, int RP, int MODE>
-__global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+__global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
 
@@ -192,14 +299,12 @@ __global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const
   const bool cross = p.kind == SIGMA_DIRS_CROSS;
 
   const int tid = threadIdx.x;
-  const int NTC = blockDim.x - 32;           // consumer threads; the last warp is the TMA producer
+  const int NTC = blockDim.x;                // every warp computes; there is no producer warp
   const int DT = NTC * CPT;                  // channels per CTA: thread t owns channels t and t + NTC (CPT = 2)
-  const int nwarps_c = NTC >> 5;
-  const bool is_producer = tid >= NTC;
   const int xc_fl = LT * DT, dbl_fl = LT * Cp;
   const int stage_fl = xc_fl + dbl_fl * (cross ? 2 : 1);
   uint64_t *full = reinterpret_cast<uint64_t *>(stages + NST * stage_fl);
-  uint64_t *empty = full + NST;
+  uint32_t *done = reinterpret_cast<uint32_t *>(full + NST);   // per-slot count of warps done with the slot
 
   const int d0 = blockIdx.x * DT;
   const int k = cross ? 0 : blockIdx.y / p.nsplit;
@@ -215,44 +320,35 @@ __global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const
 
   if (tid == 0) {
     for (int s = 0; s < NST; ++s) {
-      mbar_init(&full[s], 1);           // one arrive (the producer's expect_tx) + the TMA bytes
-      mbar_init(&empty[s], nwarps_c);   // one arrive per consumer warp
+      mbar_init(&full[s], 1);           // one arrive (the requester's expect_tx) + the TMA bytes
+      done[s] = 0;
     }
     fence_mbar_init();
   }
   __syncthreads();
 
-  auto tile_coord = [&](int tau, int &o, int &i0) {
+  // One lane requests tile tau (its ring slot is known to be free): arm the slot's full barrier with the byte
+  // count and issue the 2 (3) TMA loads.
+  const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
+  auto request_tile = [&](int tau) {
+    const int it = tau - t0, st = it % NST;
+    if (SIGMA_ABL(p.ablate, 4) && it >= NST) return;
+    float *dst = stages + st * stage_fl;
     const int tm = rev ? ntiles - 1 - tau : tau;
-    o = tm / TPO;
-    i0 = (tm - o * TPO) * LT;
+    const int o = tm / TPO, i0 = (tm - o * TPO) * LT;
+    mbar_arrive_expect_tx(&full[st], tx_bytes);
+    tma_load_4d(dst, &p.m_xc[k], &full[st], d0, i0, o, b);
+    tma_load_4d(dst + xc_fl, &p.m_dbl[k], &full[st], 0, i0, o, b);
+    if (cross) tma_load_4d(dst + xc_fl + dbl_fl, &p.m_dbl[k], &full[st], 0, i0, o, bC);
   };
-
-  if (is_producer) {
-    // ===== TMA producer warp: one elected lane refills a ring slot as soon as every consumer warp released it =====
-    if (tid == NTC) {
-      tma_prefetch_desc(&p.m_xc[k]);
-      tma_prefetch_desc(&p.m_dbl[k]);
-      const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
-      for (int tau = t0; tau < t1; ++tau) {
-        const int it = tau - t0, st = it % NST;
-        if ((p.ablate & 4) && it >= NST) break;
-        mbar_wait_backoff(&empty[st], (uint32_t)(((it / NST) & 1) ^ 1));   // fresh barrier: parity 1 passes immediately
-        float *dst = stages + st * stage_fl;
-        int o, i0;
-        tile_coord(tau, o, i0);
-        mbar_arrive_expect_tx(&full[st], tx_bytes);
-        tma_load_4d(dst, &p.m_xc[k], &full[st], d0, i0, o, b);
-        tma_load_4d(dst + xc_fl, &p.m_dbl[k], &full[st], 0, i0, o, b);
-        if (cross) tma_load_4d(dst + xc_fl + dbl_fl, &p.m_dbl[k], &full[st], 0, i0, o, bC);
-      }
-    }
-    return;
+  if (tid == 0) {
+    tma_prefetch_desc(&p.m_xc[k]);
+    tma_prefetch_desc(&p.m_dbl[k]);
+    for (int tau = t0; tau < min(t1, t0 + NST); ++tau) request_tile(tau);
   }
 
-  // ===== consumer warps: CPT channels per thread, all N states of each in registers =====
+  // ===== CPT channels per thread, all N states of each in registers =====
   Ss2dThread<N, CPT, RP> t;
-  t.ch = tid;
   t.ablate = p.ablate;
   float *carry_row[CPT];
 #pragma unroll
@@ -267,7 +363,10 @@ __global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const
     }
 #pragma unroll
     for (int r = 0; r < RP; ++r) t.W[c][r] = (t.ok[c] && r < p.R) ? p.dtw[wd * p.R + r] : 0.f;
-    t.bias[c] = t.ok[c] ? p.dtb[wd] : 0.f;
+    {
+      const float bias = t.ok[c] ? p.dtb[wd] : 0.f;
+      asm volatile("mov.b64 %0, {%1, %2};" : "=l"(t.bias2[c]) : "f"(bias), "f"(0.f));   // opaque: stays a register pair
+    }
     t.Dv[c] = t.ok[c] ? p.Ds[wd] : 0.f;
     t.sumdl[c] = 0.f;
     carry_row[c] = nullptr;
@@ -279,30 +378,20 @@ __global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const
       }
     }
   }
-  float *ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + min(d0 + tid, p.D - 1);
-  const long long istride = p.istride[k], ostride = p.ostride[k];
 
-  for (int tau = t0; tau < t1; ++tau) {
-    const int it = tau - t0;
-    const int st = it % NST;
-    if (!((p.ablate & 4) && it >= NST)) mbar_wait(&full[st], (uint32_t)((it / NST) & 1));
+  Ss2dWalk<N, CPT, RP> w;
+  w.stages = stages; w.full = full; w.done = done;
+  w.ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + min(d0 + tid, p.D - 1);
+  w.istride = p.istride[k]; w.ostride = p.ostride[k];
+  w.stage_fl = stage_fl; w.xc_fl = xc_fl; w.dbl_fl = dbl_fl; w.DT = DT;
+  w.nwarps = NTC >> 5; w.lane = tid & 31; w.ch = tid;
+  w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I;
+  w.cross = cross; w.rev = rev;
 
-    const float *sXC = stages + st * stage_fl;
-    const float *sDB = sXC + xc_fl;
-    const float *sDC = cross ? sDB + dbl_fl : sDB;
-    int o, i0;
-    tile_coord(tau, o, i0);
-    const int npos = min(LT, I - i0);
-    float *yrow = ybase + (long long)o * ostride + (long long)i0 * istride;
+  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true>(t, w, request_tile);
+  else     walk_tiles<N, CPT, RP, WITH_Y, false>(t, w, request_tile);
 
-    if (rev) scan_tile<N, CPT, RP, WITH_Y, true>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
-    else     scan_tile<N, CPT, RP, WITH_Y, false>(t, sXC, sDB, sDC, yrow, istride, DT, npos);
-
-    __syncwarp();
-    if ((tid & 31) == 0 && !(p.ablate & 4)) mbar_arrive(&empty[st]);   // this warp is done with ring slot st
-  }
-
-  if (MODE == MODE_SUMMARY || (p.ablate & 1)) {
+  if (MODE == MODE_SUMMARY || SIGMA_ABL(p.ablate, 1)) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
       if (t.ok[c] && carry_row[c] != nullptr) {
@@ -317,7 +406,7 @@ __global__ void __launch_bounds__(160, (N >= 16 ? 3 : 4)) ss2d_scan_kernel(const
 }
 
 // host-side launcher for one (N, CPT, RP) instantiation; defined per RP in ss2d_scan_rp*.cu.
-// `nthreads` = consumer threads per CTA (each owning CPT channels); the launcher adds the producer warp.
+// `nthreads` = threads per CTA (each owning CPT channels).
 template <int N, int CPT, int RP>
 int ss2d_launch(const Ss2dParams &p, int nthreads, cudaStream_t stream);
 

@@ -115,7 +115,7 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
     const int v = atoi(e);
     if (v == 1 || v == 2) cpt = v;
   }
-  int maxw = 4;  // <= 4 consumer warps + 1 producer per CTA measured best on B200 (profiles/r01_scan_variants.txt)
+  int maxw = 4;  // warps per CTA (Ss2dCfg::MAXW; the kernels' register budget assumes 128 threads)
   if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(4, atoi(e)));
   const int NW = pick_warps(D, cpt, maxw), DT = 32 * cpt * NW;
   int rc;
