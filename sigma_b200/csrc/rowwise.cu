@@ -5,6 +5,7 @@
 //   dwconv3x3_silu   : depthwise 3x3 (pad 1) + bias + SiLU on NHWC (vmamba.py:683-692,1072)
 // All are HBM-bound; loads/stores are 16-byte, rows are contiguous in the channel dimension.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -78,8 +79,108 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const RowNormParams p) {
   }
 }
 
+// Fast path for the row lengths the models use (D/4 = LPR·V float4 with LPR in {8,16,32} lanes per row):
+// a warp works on 32/LPR rows at once, every lane issues all its K·V (+V for z) 16-byte loads before the first use
+// (the generic kernel above has one load in flight per lane inside a runtime-K loop: ~45 % of HBM peak under ncu),
+// reductions are LPR-wide shuffles.  y and z are dead after this kernel: streaming loads (evict-first).
+template <int LPR, int V, int K>
+__global__ void __launch_bounds__(256) row_norm_fast_kernel(const RowNormParams p) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+  const long long row_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
+  const bool valid = row_raw < p.rows;
+  const long long row = valid ? row_raw : p.rows - 1;     // keep the warp convergent for the shuffles
+  const long long bi = row / p.rows_per_batch, ri = row - bi * p.rows_per_batch;
+  const float4 *in = reinterpret_cast<const float4 *>(p.y + bi * p.in_batch_stride + ri * p.D);
+  const long long ks4 = p.k_stride >> 2;
+  float4 x[V], kk[K > 1 ? (K - 1) * V : 1], zz[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) x[v] = __ldcs(in + l + LPR * v);
+#pragma unroll
+  for (int k = 1; k < K; ++k)
+#pragma unroll
+    for (int v = 0; v < V; ++v) kk[(k - 1) * V + v] = __ldcs(in + k * ks4 + l + LPR * v);
+  const bool has_z = p.z != nullptr;
+  if (has_z) {
+    const float4 *zr = reinterpret_cast<const float4 *>(p.z + row * p.z_row_stride);
+#pragma unroll
+    for (int v = 0; v < V; ++v) zz[v] = __ldcs(zr + l + LPR * v);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      const float4 b = kk[(k - 1) * V + v];
+      x[v].x += b.x; x[v].y += b.y; x[v].z += b.z; x[v].w += b.w;
+    }
+    s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)p.D;
+  float q = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const float dx = x[v].x - mean, dy = x[v].y - mean, dz = x[v].z - mean, dw = x[v].w - mean;
+    q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)p.D + p.eps);
+  float4 *out = reinterpret_cast<float4 *>(p.out + bi * p.out_batch_stride + ri * p.out_row_stride);
+  const float4 *gr = p.gate ? reinterpret_cast<const float4 *>(p.gate + bi * p.D) : nullptr;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int idx = l + LPR * v;
+    const float4 g = __ldg(reinterpret_cast<const float4 *>(p.gamma) + idx);
+    const float4 b = __ldg(reinterpret_cast<const float4 *>(p.beta) + idx);
+    float4 o;
+    o.x = fmaf((x[v].x - mean) * rstd, g.x, b.x);
+    o.y = fmaf((x[v].y - mean) * rstd, g.y, b.y);
+    o.z = fmaf((x[v].z - mean) * rstd, g.z, b.z);
+    o.w = fmaf((x[v].w - mean) * rstd, g.w, b.w);
+    if (has_z) { o.x *= silu(zz[v].x); o.y *= silu(zz[v].y); o.z *= silu(zz[v].z); o.w *= silu(zz[v].w); }
+    if (gr) {
+      const float4 gg = __ldg(gr + idx);
+      o.x *= gg.x; o.y *= gg.y; o.z *= gg.z; o.w *= gg.w;
+    }
+    if (valid) out[idx] = o;
+  }
+}
+
+template <int LPR, int V>
+static bool row_norm_fast_k(const RowNormParams &p, cudaStream_t stream) {
+  const int warps = 8, rows_per_cta = warps * (32 / LPR);
+  const unsigned grid = (unsigned)((p.rows + rows_per_cta - 1) / rows_per_cta);
+  switch (p.K) {
+    case 1: row_norm_fast_kernel<LPR, V, 1><<<grid, warps * 32, 0, stream>>>(p); return true;
+    case 2: row_norm_fast_kernel<LPR, V, 2><<<grid, warps * 32, 0, stream>>>(p); return true;
+    case 4: row_norm_fast_kernel<LPR, V, 4><<<grid, warps * 32, 0, stream>>>(p); return true;
+  }
+  return false;
+}
+
+// picks (lanes per row, float4 per lane) for D; false if D has no fast instantiation
+static bool row_norm_fast(const RowNormParams &p, cudaStream_t stream) {
+  if ((p.D & 3) || (p.k_stride & 3) || (p.in_batch_stride & 3) || (p.out_row_stride & 3) || (p.out_batch_stride & 3) ||
+      (p.z_row_stride & 3))
+    return false;
+  const int nvec = p.D >> 2;
+#define TRY(LPR, V) if (nvec == (LPR) * (V)) return row_norm_fast_k<LPR, V>(p, stream)
+  TRY(8, 2); TRY(8, 3); TRY(8, 4);
+  TRY(16, 3); TRY(16, 4);
+  TRY(32, 3); TRY(32, 4); TRY(32, 6); TRY(32, 8); TRY(32, 12); TRY(32, 16);
+#undef TRY
+  return false;
+}
+
 int row_norm_launch(const RowNormParams &p, cudaStream_t stream) {
   if (p.rows == 0) return SIGMA_OK;
+  if (row_norm_fast(p, stream)) {
+    SIGMA_CHECK_LAUNCH();
+    return SIGMA_OK;
+  }
   const int nvec = p.D >> 2;
   const int warps = 8;
   const unsigned grid = (unsigned)((p.rows + warps - 1) / warps);
@@ -168,9 +269,18 @@ __global__ void __launch_bounds__(256) dwconv3x3_silu_kernel(const float *__rest
   }
 }
 
+int dwconv3x3_silu_tma_launch(const float *x, long long x_row_stride, long long x_batch_stride, const float *w,
+                              const float *bias, float *y, long long y_batch_stride, int batch, int H, int W, int D,
+                              cudaStream_t stream);   // dwconv_tma.cu
+
 int dwconv3x3_silu_launch(const float *x, long long x_row_stride, long long x_batch_stride, const float *w,
                           const float *bias, float *y, long long y_batch_stride, int batch, int H, int W, int D,
                           cudaStream_t stream) {
+  static const bool direct = getenv("SIGMA_DWCONV_DIRECT") != nullptr;   // A/B switch: the first (L1-windowed) kernel
+  if (!direct) {
+    const int rc = dwconv3x3_silu_tma_launch(x, x_row_stride, x_batch_stride, w, bias, y, y_batch_stride, batch, H, W, D, stream);
+    if (rc != 1) return rc;
+  }
   const long long total = (long long)batch * H * ((W + DW_WB - 1) / DW_WB);
   if (total == 0) return SIGMA_OK;
   dim3 grid((D + DW_CH - 1) / DW_CH, (unsigned)((total + DW_GROUPS_PER_CTA - 1) / DW_GROUPS_PER_CTA));
