@@ -146,7 +146,8 @@ int sigma_merge_norm_gate_fwd(const float *y, int K, int64_t k_stride, int64_t i
                               int64_t rows_per_batch, int D, float eps, void *stream);
 
 /* UpsampleExpand tail (MambaDecoder.py:47-49): y = LayerNorm(bilinear x2 (align_corners=False) of x); x (batch,H,W,C),
- * y (batch,2H,2W,C).  One pass: the upsampled tensor is never materialised un-normalised.              */
+ * y (batch,2H,2W,C).  One pass: the upsampled tensor is never materialised un-normalised.
+ * w == b == NULL: plain bilinear x2 without the LayerNorm (FinalUpsample_X4's first interpolate, MambaDecoder.py:92). */
 int sigma_upsample2x_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,
                               float eps, void *stream);
 

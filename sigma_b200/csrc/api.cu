@@ -304,9 +304,10 @@ int sigma_ss2d_scan_fwd_split(int kind, const float *xc, const float *xdbl, cons
 
 int sigma_upsample2x_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,
                               float eps, void *stream) {
-  SIGMA_CHECK_ARG(x && w && b && y, "sigma_upsample2x_norm_fwd: null pointer");
+  SIGMA_CHECK_ARG(x && y && ((w && b) || (!w && !b)), "sigma_upsample2x_norm_fwd: null pointer (w and b may be NULL together)");
   SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "sigma_upsample2x_norm_fwd: bad sizes");
   SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(y), "sigma_upsample2x_norm_fwd: pointers must be 16-byte aligned");
+  if (!w) return upsample2x_norm_launch(x, nullptr, nullptr, nullptr, 0, y, batch, H, W, C, eps, (cudaStream_t)stream);
   return upsample2x_norm_launch(x, w, b, nullptr, 0, y, batch, H, W, C, eps, (cudaStream_t)stream);
 }
 

@@ -412,10 +412,163 @@ __global__ void __launch_bounds__(256) upsample2x_norm_kernel(const float *__res
   }
 }
 
+// ---- plain bilinear x2 (no norm), channels-last: one thread per (output pixel, 4 channels) ----
+__global__ void __launch_bounds__(256) upsample2x_plain_kernel(const float *__restrict__ in, float *__restrict__ out, int B,
+                                                              int Hin, int Win, int C) {
+  const int nvec = C >> 2, Ho = 2 * Hin, Wo = 2 * Win;
+  const long long total = (long long)B * Ho * Wo * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % nvec);
+    const long long pix = i / nvec;
+    const int b = (int)(pix / ((long long)Ho * Wo));
+    const int rem = (int)(pix - (long long)b * Ho * Wo);
+    const int oh = rem / Wo, ow = rem - oh * Wo;
+    int h0, h1, w0, w1;
+    float fh, fw;
+    bilinear2x_taps(oh, Hin, h0, h1, fh);
+    bilinear2x_taps(ow, Win, w0, w1, fw);
+    const float4 *base = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C) + q;
+    const float4 a = __ldg(base + ((long long)h0 * Win + w0) * nvec), bq = __ldg(base + ((long long)h0 * Win + w1) * nvec);
+    const float4 c = __ldg(base + ((long long)h1 * Win + w0) * nvec), d = __ldg(base + ((long long)h1 * Win + w1) * nvec);
+    float4 o;   // same association as PyTorch's upsample_bilinear2d
+    o.x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
+    o.y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
+    o.z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
+    o.w = (1.f - fh) * ((1.f - fw) * a.w + fw * bq.w) + fh * ((1.f - fw) * c.w + fw * d.w);
+    reinterpret_cast<float4 *>(out)[i] = o;
+  }
+}
+
+// ---- bilinear x2 -> LayerNorm -> (NCLS, C) head, for C = 4·LPR·V: a warp works on 32/LPR output pixels at once
+// (LPR lanes per pixel, V float4 per lane), so LayerNorm and the NCLS dot products reduce with log2(LPR) shuffles
+// for 32/LPR pixels instead of 5 per pixel; the head weights are read from shared memory (LDS.128, 128-byte rows).
+// The generic kernel above spends 55 warp shuffles per pixel: 5 ms for 32 x 480 x 640 pixels. ----
+template <int LPR, int V, int NCLS>
+__global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
+                                                                        const float *__restrict__ beta, const float *__restrict__ wcls,
+                                                                        float *__restrict__ out, int B, int Hin, int Win, float eps,
+                                                                        int passes) {
+  constexpr int RPW = 32 / LPR, C4 = LPR * V, C = 4 * C4, PPP = 8 * RPW;   // pixels per pass of the 8-warp CTA
+  __shared__ __align__(16) float sw[NCLS][C];
+  __shared__ float slog[NCLS][PPP];
+  for (int i = threadIdx.x; i < NCLS * C; i += blockDim.x) sw[i / C][i % C] = wcls[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
+  const int Ho = 2 * Hin, Wo = 2 * Win;
+  const long long HWo = (long long)Ho * Wo, npix = (long long)B * HWo;
+  float4 g[V], bt[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    g[v] = __ldg(reinterpret_cast<const float4 *>(gamma) + l + LPR * v);
+    bt[v] = __ldg(reinterpret_cast<const float4 *>(beta) + l + LPR * v);
+  }
+  for (int pass = 0; pass < passes; ++pass) {
+    const long long p0 = ((long long)blockIdx.x * passes + pass) * PPP;
+    if (p0 >= npix) break;
+    const long long pix = min(p0 + warp * RPW + sub, npix - 1);
+    const int b = (int)(pix / HWo);
+    const int rem = (int)(pix - (long long)b * HWo);
+    const int oh = rem / Wo, ow = rem - oh * Wo;
+    int h0, h1, w0, w1;
+    float fh, fw;
+    bilinear2x_taps(oh, Hin, h0, h1, fh);
+    bilinear2x_taps(ow, Win, w0, w1, fw);
+    const float4 *base = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C) + l;
+    const float4 *r00 = base + ((long long)h0 * Win + w0) * C4, *r01 = base + ((long long)h0 * Win + w1) * C4;
+    const float4 *r10 = base + ((long long)h1 * Win + w0) * C4, *r11 = base + ((long long)h1 * Win + w1) * C4;
+    float4 x[V];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float4 a = __ldg(r00 + LPR * v), bq = __ldg(r01 + LPR * v), c = __ldg(r10 + LPR * v), d = __ldg(r11 + LPR * v);
+      x[v].x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
+      x[v].y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
+      x[v].z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
+      x[v].w = (1.f - fh) * ((1.f - fw) * a.w + fw * bq.w) + fh * ((1.f - fw) * c.w + fw * d.w);
+      s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float dx = x[v].x - mean, dy = x[v].y - mean, dz = x[v].z - mean, dw = x[v].w - mean;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    float acc[NCLS];
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      float4 o;
+      o.x = fmaf((x[v].x - mean) * rstd, g[v].x, bt[v].x);
+      o.y = fmaf((x[v].y - mean) * rstd, g[v].y, bt[v].y);
+      o.z = fmaf((x[v].z - mean) * rstd, g[v].z, bt[v].z);
+      o.w = fmaf((x[v].w - mean) * rstd, g[v].w, bt[v].w);
+#pragma unroll
+      for (int c = 0; c < NCLS; ++c) {
+        const float4 wv = *reinterpret_cast<const float4 *>(&sw[c][4 * (l + LPR * v)]);
+        acc[c] = fmaf(o.x, wv.x, fmaf(o.y, wv.y, fmaf(o.z, wv.z, fmaf(o.w, wv.w, acc[c]))));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) {
+      float a = acc[c];
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+      if (l == 0) slog[c][warp * RPW + sub] = a;
+    }
+    __syncthreads();
+    // PPP consecutive pixels x NCLS classes -> NCHW, contiguous runs per class
+    for (int i = threadIdx.x; i < NCLS * PPP; i += blockDim.x) {
+      const int c = i / PPP, j = i % PPP;
+      const long long pp = p0 + j;
+      if (pp < npix) {
+        const long long bb = pp / HWo, r = pp - bb * HWo;
+        out[(bb * NCLS + c) * HWo + r] = slog[c][j];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NCLS>
+static bool upsample2x_norm_head_fast(const float *in, const float *gamma, const float *beta, const float *wcls, float *out,
+                                      int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
+  if (NCLS == 0 || NCLS > 24) return false;
+  const long long npix = 4LL * B * Hin * Win;
+  const int passes = 8;
+#define TRY(LPR, V)                                                                                                         \
+  if (C == 4 * (LPR) * (V)) {                                                                                               \
+    const long long ppc = (long long)passes * 8 * (32 / (LPR));                                                             \
+    upsample2x_norm_head_fast_kernel<LPR, V, (NCLS > 0 && NCLS <= 24 ? NCLS : 1)>                                           \
+        <<<(unsigned)((npix + ppc - 1) / ppc), 256, 0, stream>>>(in, gamma, beta, wcls, out, B, Hin, Win, eps, passes);     \
+    return true;                                                                                                            \
+  }
+  TRY(8, 2) TRY(8, 3) TRY(8, 4) TRY(16, 3) TRY(16, 4)
+#undef TRY
+  return false;
+}
+
 template <int NCLS>
 static int upsample2x_norm_dispatch(const float *in, const float *gamma, const float *beta, const float *wcls, float *out,
                                     int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
   const long long npix = 4LL * B * Hin * Win;
+  if (NCLS == 0 && gamma == nullptr) {   // plain bilinear x2
+    const long long total = npix * (C >> 2);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+    upsample2x_plain_kernel<<<grid, 256, 0, stream>>>(in, out, B, Hin, Win, C);
+    SIGMA_CHECK_LAUNCH();
+    return SIGMA_OK;
+  }
+  if (NCLS > 0 && upsample2x_norm_head_fast<NCLS>(in, gamma, beta, wcls, out, B, Hin, Win, C, eps, stream)) {
+    SIGMA_CHECK_LAUNCH();
+    return SIGMA_OK;
+  }
   const int ppc = NCLS > 0 ? 32 : 8;
   const unsigned grid = (unsigned)((npix + ppc - 1) / ppc);
   const int nvec = C >> 2;

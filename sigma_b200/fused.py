@@ -248,12 +248,13 @@ def ln_nhwc(ln, x):
 
 
 def upsample2x_norm(x, ln):
-    """LayerNorm(bilinear x2 (x)) in one pass (UpsampleExpand tail, MambaDecoder.py:47-49)."""
+    """LayerNorm(bilinear x2 (x)) in one pass (UpsampleExpand tail, MambaDecoder.py:47-49); ln=None: plain bilinear x2."""
     x = x.contiguous()
     B, H, W, C = x.shape
     y = torch.empty((B, 2 * H, 2 * W, C), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().sigma_upsample2x_norm_fwd(_p(x), _p(ln.weight), _p(ln.bias), _p(y), B, H, W, C, float(ln.eps),
-                                                     _stream()), "sigma_upsample2x_norm_fwd")
+    wp, bp, eps = (_p(ln.weight), _p(ln.bias), float(ln.eps)) if ln is not None else (None, None, 0.0)
+    _lib.check(_lib.lib().sigma_upsample2x_norm_fwd(_p(x), wp, bp, _p(y), B, H, W, C, eps, _stream()),
+               "sigma_upsample2x_norm_fwd")
     return y
 
 
@@ -327,5 +328,5 @@ def final_head(dec, x):
     B, H, W, C = x.shape
     t = linear(x.reshape(B * H * W, C), dec.up.linear1.weight)
     t = linear(t, dec.up.linear2.weight).view(B, H, W, C)
-    t = F.interpolate(t.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    t = upsample2x_norm(t, None)   # plain bilinear x2
     return upsample2x_norm_head(t, dec.up.norm, dec.output)

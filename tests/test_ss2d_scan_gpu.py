@@ -143,7 +143,8 @@ def test_merge_norm_gate():
     assert_close(out, ref, 2e-5, 5e-5, "merge+norm+gate")
 
 
-@pytest.mark.parametrize("B,H,W,C,ncls", [(2, 5, 7, 32, 0), (1, 30, 40, 192, 0), (2, 6, 4, 96, 9), (1, 15, 20, 32, 5), (1, 3, 3, 128, 40)])
+@pytest.mark.parametrize("B,H,W,C,ncls", [(2, 5, 7, 32, 0), (1, 30, 40, 192, 0), (2, 6, 4, 96, 9), (1, 15, 20, 32, 5), (1, 3, 3, 128, 40),
+                                          (3, 7, 5, 96, 9), (2, 9, 11, 128, 9), (1, 13, 3, 64, 2), (1, 6, 5, 192, 19), (1, 4, 4, 256, 12)])
 def test_upsample2x_norm_and_head(B, H, W, C, ncls):
     from sigma_b200 import fused
     x = P.randn(S, f"up/{B}/{H}/{W}/{C}", (B, H, W, C))
@@ -161,6 +162,16 @@ def test_upsample2x_norm_and_head(B, H, W, C, ncls):
         else:
             got = fused.upsample2x_norm(x.cuda(), ln.cuda())
     assert_close(got, ref, 2e-5, 5e-5, f"upsample2x_norm ncls={ncls}")
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 5, 7, 32), (1, 30, 40, 96), (3, 1, 1, 8)])
+def test_upsample2x_plain(B, H, W, C):
+    """w = b = NULL: plain bilinear x2 (FinalUpsample_X4's first interpolate, MambaDecoder.py:92)."""
+    from sigma_b200 import fused
+    x = P.randn(S, f"upp/{B}/{H}/{W}/{C}", (B, H, W, C))
+    ref = torch.nn.functional.interpolate(x.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=False)
+    got = fused.upsample2x_norm(x.cuda(), None)
+    assert_close(got, ref.permute(0, 2, 3, 1), 1e-6, 1e-6, "upsample2x plain")
 
 
 def test_pool_and_scale_add():
