@@ -677,7 +677,9 @@ class RGBXTransformer(nn.Module):
         for i in range(4):
             o_r, o_x = outs[i][:B], outs[i][B:]
             c_r, c_x = self.cross_mamba[i](o_r, o_x)
-            fused.append(self.channel_attn_mamba[i](c_r, c_x).permute(0, 3, 1, 2).contiguous())
+            # NCHW-shaped like the reference's outputs, channels_last in memory: the decoder (and any 1x1 conv) reads it
+            # without a transposing copy
+            fused.append(self.channel_attn_mamba[i](c_r, c_x).permute(0, 3, 1, 2))
         return fused
 
     def forward(self, x_rgb, x_e):
