@@ -36,8 +36,8 @@ namespace sigma {
 template <int N>
 struct Ss2dCfg {
   static constexpr int G = N >= 16 ? 4 : 8;       // positions per software-pipelined group (measured: 8/16 lose at N=16, 16 loses at N=4)
-  static constexpr int LT = N >= 16 ? 16 : 32;    // scan positions per tile (multiple of G)
-  static constexpr int NST = N >= 16 ? 4 : 3;     // TMA ring depth
+  static constexpr int LT = N >= 16 ? 16 : 32;    // scan positions per tile (multiple of G; measured: 16 loses at N=4)
+  static constexpr int MAX_NST = 8;               // TMA ring depth is chosen on the host (Ss2dParams::nst), up to this
   static constexpr int MAXW = 4;                  // warps per CTA
   static constexpr int CTAS = 3;                  // resident CTAs per SM the register budget is set for (168 regs)
 };
@@ -51,6 +51,7 @@ struct alignas(64) Ss2dParams {
   int I[4], O[4], rev[4];
   long long istride[4], ostride[4];   // y element strides of the inner / outer walk index
   int nsplit, tiles_per_split;
+  int nst;     // TMA ring depth: as many LT-position stages as fit next to CTAS-1 other CTAs in shared memory
   int ablate;  // timing experiments, only in builds with -DSIGMA_SCAN_ABLATION (SIGMA_SCAN_ABLATE env):
                // 1 = no y store, 2 = no per-group prologue, 4 = no TMA reload
 };
@@ -196,7 +197,7 @@ struct Ss2dWalk {
   float *ybase;
   long long istride, ostride;
   int stage_fl, xc_fl, dbl_fl, DT, nwarps, lane, ch;
-  int t0, t1, TPO, ntiles, I;
+  int t0, t1, TPO, ntiles, I, nst;
   bool cross, rev;
 };
 
@@ -205,32 +206,39 @@ struct Ss2dWalk {
 // last group of its tile — so no prologue is exposed at a tile boundary and none is computed twice.
 template <int N, int CPT, int RP, bool WITH_Y, bool REV, typename Request>
 __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2dWalk<N, CPT, RP> &w, Request &&request_tile) {
-  constexpr int G = Ss2dCfg<N>::G, LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
+  constexpr int G = Ss2dCfg<N>::G, LT = Ss2dCfg<N>::LT;
   constexpr int Cp = 2 * N + RP;
   const int ycs = w.DT / CPT;
 
+  // ring slot / phase and (outer index, inner tile) of the tile being opened advance incrementally: no division
+  // or modulo per tile.  Tiles are walked in ascending tau; reversed directions map tau -> ntiles-1-tau.
   struct Tile { const float *sXC, *sDB, *sDC; float *yrow; int npos, ng; };
-  auto open_tile = [&](int tau) {   // waits for the tile's TMA bytes; returns its pointers
-    const int it = tau - w.t0, st = it % NST;
-    if (!(SIGMA_ABL(t.ablate, 4) && it >= NST)) mbar_spin(&w.full[st], (uint32_t)((it / NST) & 1));
+  int ost = 0, oph = 0;                                  // slot and phase parity of the next tile to open
+  int tm0 = w.rev ? w.ntiles - 1 - w.t0 : w.t0;          // memory-order tile index of tile t0
+  int oo = tm0 / w.TPO, oti = tm0 - oo * w.TPO;          // its (outer index, inner tile)
+  auto open_tile = [&]() {   // waits for the next tile's TMA bytes; returns its pointers and advances the cursor
+    if (!(SIGMA_ABL(t.ablate, 4) && oph)) mbar_spin(&w.full[ost], (uint32_t)oph);
     Tile T;
-    T.sXC = w.stages + st * w.stage_fl;
+    T.sXC = w.stages + ost * w.stage_fl;
     T.sDB = T.sXC + w.xc_fl;
     T.sDC = w.cross ? T.sDB + w.dbl_fl : T.sDB;
-    const int tm = w.rev ? w.ntiles - 1 - tau : tau;
-    const int o = tm / w.TPO, i0 = (tm - o * w.TPO) * LT;
+    const int i0 = oti * LT;
     T.npos = min(LT, w.I - i0);
     T.ng = (T.npos + G - 1) / G;
-    T.yrow = w.ybase + (long long)o * w.ostride + (long long)i0 * w.istride;
+    T.yrow = w.ybase + (long long)oo * w.ostride + (long long)i0 * w.istride;
+    if (++ost == w.nst) { ost = 0; oph ^= 1; }
+    if (w.rev) { if (--oti < 0) { oti = w.TPO - 1; --oo; } }
+    else       { if (++oti == w.TPO) { oti = 0; ++oo; } }
     return T;
   };
 
   if (w.t0 >= w.t1) return;
-  Tile cur = open_tile(w.t0);
+  Tile cur = open_tile();
   int j = REV ? cur.ng - 1 : 0;   // walking backwards, a ragged group (npos % G) comes first
   float dl[CPT][G], u[CPT][G];
   group_prologue<N, CPT, RP, G>(t, cur.sXC + j * G * w.DT + w.ch, cur.sDB + j * G * Cp + 2 * N, w.DT, dl, u);
 
+  int rst = 0;                    // ring slot of the tile being processed
   for (int tau = w.t0; tau < w.t1; ++tau) {
     Tile nxt = cur;
     int jn = j;
@@ -243,7 +251,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
         px = cur.sXC + jn * G * w.DT + w.ch;
         pd = cur.sDB + jn * G * Cp + 2 * N;
       } else if (tau + 1 < w.t1) {
-        nxt = open_tile(tau + 1);
+        nxt = open_tile();
         jn = REV ? nxt.ng - 1 : 0;
         px = nxt.sXC + jn * G * w.DT + w.ch;
         pd = nxt.sDB + jn * G * Cp + 2 * N;
@@ -279,19 +287,20 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
     }
     // this warp is done with the ring slot; the last of the CTA's warps to get here refills it
     __syncwarp();
-    if (w.lane == 0 && tau + NST < w.t1) {
-      const int st = (tau - w.t0) % NST;
-      const uint32_t old = smem_inc_acq_rel(&w.done[st]);
-      if ((old + 1) % (uint32_t)w.nwarps == 0) request_tile(tau + NST);
+    if (w.lane == 0 && tau + w.nst < w.t1) {
+      const uint32_t old = smem_inc_acq_rel(&w.done[rst]);
+      if ((old + 1) % (uint32_t)w.nwarps == 0) request_tile(tau + w.nst, rst);
     }
+    if (++rst == w.nst) rst = 0;
     cur = nxt;
   }
 }
 
 template <int N, int CPT, int RP, int MODE>
 __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
-  constexpr int LT = Ss2dCfg<N>::LT, NST = Ss2dCfg<N>::NST;
+  constexpr int LT = Ss2dCfg<N>::LT;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
+  const int NST = p.nst;
 
   extern __shared__ __align__(1024) unsigned char smem_raw[];  // TMA destinations need 128-byte alignment
   float *stages = reinterpret_cast<float *>(smem_raw);
@@ -330,9 +339,8 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
   // One lane requests tile tau (its ring slot is known to be free): arm the slot's full barrier with the byte
   // count and issue the 2 (3) TMA loads.
   const uint32_t tx_bytes = (uint32_t)(stage_fl * sizeof(float));
-  auto request_tile = [&](int tau) {
-    const int it = tau - t0, st = it % NST;
-    if (SIGMA_ABL(p.ablate, 4) && it >= NST) return;
+  auto request_tile = [&](int tau, int st) {
+    if (SIGMA_ABL(p.ablate, 4) && tau - t0 >= NST) return;
     float *dst = stages + st * stage_fl;
     const int tm = rev ? ntiles - 1 - tau : tau;
     const int o = tm / TPO, i0 = (tm - o * TPO) * LT;
@@ -344,7 +352,7 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
   if (tid == 0) {
     tma_prefetch_desc(&p.m_xc[k]);
     tma_prefetch_desc(&p.m_dbl[k]);
-    for (int tau = t0; tau < min(t1, t0 + NST); ++tau) request_tile(tau);
+    for (int tau = t0; tau < min(t1, t0 + NST); ++tau) request_tile(tau, tau - t0);
   }
 
   // ===== CPT channels per thread, all N states of each in registers =====
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
   w.istride = p.istride[k]; w.ostride = p.ostride[k];
   w.stage_fl = stage_fl; w.xc_fl = xc_fl; w.dbl_fl = dbl_fl; w.DT = DT;
   w.nwarps = NTC >> 5; w.lane = tid & 31; w.ch = tid;
-  w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I;
+  w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I; w.nst = NST;
   w.cross = cross; w.rev = rev;
 
   if (rev) walk_tiles<N, CPT, RP, WITH_Y, true>(t, w, request_tile);

@@ -170,6 +170,18 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   p.tiles_per_split = (max_tiles + nsplit - 1) / nsplit;
   p.nsplit = nsplit;
 
+  {
+    // TMA ring depth: as many stages as fit without lowering the register-limited occupancy (227 KB per SM, 1 KB
+    // reserved per CTA).
+    // Deep rings matter: a tile is requested when the LAST warp releases its slot and needed by the FIRST warp
+    // nst-1 tiles later; with 3-4 stages the warps spun on the full barrier ~80 times per tile (ncu, round 1).
+    const size_t stage = ((size_t)LT * DT + (size_t)LT * Cp * (kind == SIGMA_DIRS_CROSS ? 2 : 1)) * sizeof(float);
+    // resident CTAs per SM by registers (168 per thread under __launch_bounds__(128, 3)): 3 / 4 / 6 / 12 for 4 / 3 / 2 / 1 warps
+    const int ctas_sm = std::max(Ss2dCfg<16>::CTAS, std::min(12, 65536 / (32 * NW * 168)));
+    const size_t budget = (227 * 1024) / ctas_sm - 1024 - 128;
+    p.nst = (int)std::max<size_t>(2, std::min<size_t>(Ss2dCfg<16>::MAX_NST, budget / stage));
+    if (const char *e = getenv("SIGMA_SCAN_NST")) p.nst = std::max(2, std::min(Ss2dCfg<16>::MAX_NST, atoi(e)));
+  }
   const int nthreads = 32 * NW;
   switch (N * 8 + cpt) {
     case 4 * 8 + 1: return dispatch_rp<4, 1>(p, nthreads, stream);
