@@ -127,6 +127,18 @@ int sigma_ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const floa
 int sigma_layernorm_fwd(const float *x, const float *w, const float *b, float *y, int64_t rows,
                         int C, float eps, void *stream);
 
+/* PatchMerging2D front half (vmamba.py:619-633): y[b,i,j,:] = LayerNorm(cat(x[b,2i,2j], x[b,2i+1,2j], x[b,2i,2j+1],
+ * x[b,2i+1,2j+1])) over 4C channels, zero rows beyond an odd H / W (F.pad).  x (batch,H,W,C) -> y (batch,⌈H/2⌉,⌈W/2⌉,4C);
+ * the gather is index math inside the LayerNorm kernel (no concatenated tensor).  4C must be 32·k·{2,3,4,6,8,12,16}-shaped
+ * (every Sigma width is).                                                                    */
+int sigma_patch_merge_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W,
+                               int C, float eps, void *stream);
+
+/* PatchExpand back half (MambaDecoder.py:24-30): x is the expand Linear's output (batch,H,W,2,2,C) ("b h w (p1 p2 c)"),
+ * y[b,2h+p1,2w+p2,:] = LayerNorm(x[b,h,w,p1,p2,:]); y (batch,2H,2W,C).  The pixel shuffle is the store address.   */
+int sigma_pixel_shuffle_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W,
+                                 int C, float eps, void *stream);
+
 /* depthwise 3x3 conv (pad 1) + bias + SiLU, channels-last (vmamba.py:683-692,1072).
  * x: position rows x_row_stride floats apart, images x_batch_stride apart (so the x half of
  * in_proj's (.., 2D) output is read in place); w is the nn.Conv2d weight (D,1,3,3) contiguous;

@@ -36,6 +36,8 @@ SIGNATURES = {
     "sigma_merge_norm_gate_fwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_void_p]),
     "sigma_upsample2x_norm_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
+    "sigma_patch_merge_norm_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
+    "sigma_pixel_shuffle_norm_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_float, c_void_p]),
     "sigma_upsample2x_norm_head_fwd": (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "sigma_pool_avgmax_partial_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "sigma_scale_add_fwd": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_int, c_void_p]),

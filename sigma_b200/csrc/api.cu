@@ -229,6 +229,28 @@ int sigma_layernorm_fwd(const float *x, const float *w, const float *b, float *y
   return row_norm_launch(p, (cudaStream_t)stream);
 }
 
+int sigma_patch_merge_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,
+                               float eps, void *stream) {
+  SIGMA_CHECK_ARG(x && w && b && y, "sigma_patch_merge_norm_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "sigma_patch_merge_norm_fwd: bad sizes");
+  SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(y), "sigma_patch_merge_norm_fwd: pointers must be 16-byte aligned");
+  const int64_t rows = (int64_t)batch * ((H + 1) / 2) * ((W + 1) / 2);
+  RowNormParams p{x, 0, 1, w, b, nullptr, 0, nullptr, y, rows, rows, 0, 0, 4 * C, 4 * C, eps};
+  p.mode = 1; p.gH = H; p.gW = W;
+  return row_norm_launch(p, (cudaStream_t)stream);
+}
+
+int sigma_pixel_shuffle_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,
+                                 float eps, void *stream) {
+  SIGMA_CHECK_ARG(x && w && b && y, "sigma_pixel_shuffle_norm_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "sigma_pixel_shuffle_norm_fwd: bad sizes");
+  SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(y), "sigma_pixel_shuffle_norm_fwd: pointers must be 16-byte aligned");
+  const int64_t rows = (int64_t)batch * H * W * 4;
+  RowNormParams p{x, 0, 1, w, b, nullptr, 0, nullptr, y, rows, rows, 0, 0, C, C, eps};
+  p.mode = 2; p.gH = H; p.gW = W;
+  return row_norm_launch(p, (cudaStream_t)stream);
+}
+
 int sigma_merge_norm_gate_fwd(const float *y, int K, int64_t k_stride, int64_t in_batch_stride, const float *gamma,
                               const float *beta, const float *z, int64_t z_row_stride, const float *gate, float *out,
                               int64_t out_batch_stride, int64_t out_row_stride, int64_t rows, int64_t rows_per_batch,

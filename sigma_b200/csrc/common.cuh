@@ -51,6 +51,12 @@ struct RowNormParams {
   long long in_batch_stride, out_batch_stride, out_row_stride;
   int D;
   float eps;
+  // row addressing mode (fast kernel only): 0 = plain rows;
+  // 1 = PatchMerging2D gather (vmamba.py:619-636): y is (batch, gH, gW, D/4), row (b,i,j) = the four pixels
+  //     (2i,2j), (2i+1,2j), (2i,2j+1), (2i+1,2j+1) concatenated, zeros beyond odd gH / gW;
+  // 2 = PatchExpand pixel shuffle (MambaDecoder.py:24-28): input rows are (b, h, w, p1, p2) sub-rows of D channels,
+  //     row lands at out (b, 2h+p1, 2w+p2)
+  int mode = 0, gH = 0, gW = 0;
 };
 
 // ---- device math ----

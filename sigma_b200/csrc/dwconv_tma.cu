@@ -98,8 +98,10 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_silu_tma_kernel(const __grid
           for (int dx = 0; dx < 3; ++dx) {
             const float4 v = win[j + dx];
             const float4 k = wt[tr * 3 + dx];
-            acc[rr][j].x = fmaf(v.x, k.x, acc[rr][j].x); acc[rr][j].y = fmaf(v.y, k.y, acc[rr][j].y);
-            acc[rr][j].z = fmaf(v.z, k.z, acc[rr][j].z); acc[rr][j].w = fmaf(v.w, k.w, acc[rr][j].w);
+            // packed fp32x2 FMAs (FFMA2): half the issue slots of 4 scalar FFMAs, identical rounding
+            const f2 lo = fma2(f2{v.x, v.y}, f2{k.x, k.y}, f2{acc[rr][j].x, acc[rr][j].y});
+            const f2 hi = fma2(f2{v.z, v.w}, f2{k.z, k.w}, f2{acc[rr][j].z, acc[rr][j].w});
+            acc[rr][j] = make_float4(lo.x, lo.y, hi.x, hi.y);
           }
         }
       }
@@ -148,7 +150,8 @@ int dwconv3x3_silu_tma_launch(const float *x, long long x_row_stride, long long 
   // persistent over spatial tiles: 2 CTAs per SM in total, channel block fastest so that the CTAs working on one
   // spatial tile (adjacent 128-byte pieces of the same pixel rows) run at the same time
   const long long slots = 148LL * 2;
-  const unsigned ny = (unsigned)std::max<long long>(1, std::min<long long>(p.ntiles, (slots + cblocks - 1) / cblocks));
+  // (never more CTAs than resident slots: a partial second wave of persistent CTAs would double the kernel time)
+  const unsigned ny = (unsigned)std::max<long long>(1, std::min<long long>(p.ntiles, slots / cblocks));
   dim3 grid(cblocks, ny);
   dwconv3x3_silu_tma_kernel<<<grid, 256, smem, stream>>>(p);
   SIGMA_CHECK_LAUNCH();

@@ -196,16 +196,29 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
       const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
       const int acc = (int)(tc & 1);
       const int row = m0 + quarter * 32 + lane;
-      mbar_wait(&acc_full[acc], (uint32_t)((tc >> 1) & 1));
-      tc_fence_after();
       const bool row_ok = row < p.M;
       const float *rrow = (p.residual && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;
+      // the residual row chunk is fetched one chunk ahead (the first one before the accumulator is even ready): a
+      // thread-per-row read is 32 sectors per request and would otherwise sit between tcgen05.ld and the store
+      float4 rpre[8];
+      auto fetch_residual = [&](int n) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          rpre[q] = (rrow && n + 4 * q < p.N) ? __ldg(reinterpret_cast<const float4 *>(rrow + n + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      if (rrow) fetch_residual(n0 + 32 * chalf);
+      mbar_wait(&acc_full[acc], (uint32_t)((tc >> 1) & 1));
+      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols);
       for (int c0 = 32 * chalf; c0 < BN; c0 += 64) {
         const int n = n0 + c0;
         if (n >= p.N) break;                          // warp-uniform
         float v[32];
         tmem_ld32(taddr + (uint32_t)c0, v);          // warp-wide
+        float4 rcur[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rcur[q] = rpre[q];
+        if (rrow && c0 + 64 < BN && n + 64 < p.N) fetch_residual(n + 64);
         float4 *dst = reinterpret_cast<float4 *>(stage_c + lane * 128);
         if (lane == 0) tma_store_wait_read<0>();     // the previous store of this warp has finished reading the buffer
         __syncwarp();
@@ -219,7 +232,7 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
               o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
             }
             if (rrow) {
-              const float4 r = __ldg(reinterpret_cast<const float4 *>(rrow + nn));
+              const float4 r = rcur[q];
               if (p.rscale) {
                 const float4 sc = __ldg(reinterpret_cast<const float4 *>(p.rscale + nn));
                 o.x = fmaf(r.x, sc.x, o.x); o.y = fmaf(r.y, sc.y, o.y); o.z = fmaf(r.z, sc.z, o.z); o.w = fmaf(r.w, sc.w, o.w);

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const RowNormParams p) {
 // a warp works on 32/LPR rows at once, every lane issues all its K·V (+V for z) 16-byte loads before the first use
 // (the generic kernel above has one load in flight per lane inside a runtime-K loop: ~45 % of HBM peak under ncu),
 // reductions are LPR-wide shuffles.  y and z are dead after this kernel: streaming loads (evict-first).
-template <int LPR, int V, int K>
+template <int LPR, int V, int K, int MODE>
 __global__ void __launch_bounds__(256) row_norm_fast_kernel(const RowNormParams p) {
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
@@ -94,8 +94,22 @@ __global__ void __launch_bounds__(256) row_norm_fast_kernel(const RowNormParams 
   const float4 *in = reinterpret_cast<const float4 *>(p.y + bi * p.in_batch_stride + ri * p.D);
   const long long ks4 = p.k_stride >> 2;
   float4 x[V], kk[K > 1 ? (K - 1) * V : 1], zz[V];
+  if (MODE == 1) {
+    // gather the 2x2 pixel block of output row (b, i, j); quadrant q of the row = pixel (2i + (q&1), 2j + (q>>1))
+    const int H2 = (p.gH + 1) >> 1, W2 = (p.gW + 1) >> 1, cq = (p.D >> 2) >> 2;   // float4 per source pixel
+    const long long b = row / ((long long)H2 * W2);
+    const int rem = (int)(row - b * H2 * W2), i = rem / W2, j = rem - i * W2;
+    const float4 *src = reinterpret_cast<const float4 *>(p.y) + b * p.gH * p.gW * cq;
 #pragma unroll
-  for (int v = 0; v < V; ++v) x[v] = __ldcs(in + l + LPR * v);
+    for (int v = 0; v < V; ++v) {
+      const int idx = l + LPR * v, q = idx / cq, c4 = idx - q * cq;
+      const int hh = 2 * i + (q & 1), ww = 2 * j + (q >> 1);
+      x[v] = (hh < p.gH && ww < p.gW) ? __ldg(src + ((long long)hh * p.gW + ww) * cq + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int v = 0; v < V; ++v) x[v] = __ldcs(in + l + LPR * v);
+  }
 #pragma unroll
   for (int k = 1; k < K; ++k)
 #pragma unroll
@@ -129,6 +143,12 @@ __global__ void __launch_bounds__(256) row_norm_fast_kernel(const RowNormParams 
   for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = rsqrtf(q / (float)p.D + p.eps);
   float4 *out = reinterpret_cast<float4 *>(p.out + bi * p.out_batch_stride + ri * p.out_row_stride);
+  if (MODE == 2) {
+    const int p2 = (int)(row & 1), p1 = (int)((row >> 1) & 1);
+    const long long pix = row >> 2, b = pix / ((long long)p.gH * p.gW);
+    const int rem = (int)(pix - b * p.gH * p.gW), h = rem / p.gW, w = rem - h * p.gW;
+    out = reinterpret_cast<float4 *>(p.out + (((b * 2 * p.gH + 2 * h + p1) * 2 * p.gW) + 2 * w + p2) * p.D);
+  }
   const float4 *gr = p.gate ? reinterpret_cast<const float4 *>(p.gate + bi * p.D) : nullptr;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -153,10 +173,13 @@ template <int LPR, int V>
 static bool row_norm_fast_k(const RowNormParams &p, cudaStream_t stream) {
   const int warps = 8, rows_per_cta = warps * (32 / LPR);
   const unsigned grid = (unsigned)((p.rows + rows_per_cta - 1) / rows_per_cta);
+  if (p.mode == 1 && p.K == 1) { row_norm_fast_kernel<LPR, V, 1, 1><<<grid, warps * 32, 0, stream>>>(p); return true; }
+  if (p.mode == 2 && p.K == 1) { row_norm_fast_kernel<LPR, V, 1, 2><<<grid, warps * 32, 0, stream>>>(p); return true; }
+  if (p.mode != 0) return false;
   switch (p.K) {
-    case 1: row_norm_fast_kernel<LPR, V, 1><<<grid, warps * 32, 0, stream>>>(p); return true;
-    case 2: row_norm_fast_kernel<LPR, V, 2><<<grid, warps * 32, 0, stream>>>(p); return true;
-    case 4: row_norm_fast_kernel<LPR, V, 4><<<grid, warps * 32, 0, stream>>>(p); return true;
+    case 1: row_norm_fast_kernel<LPR, V, 1, 0><<<grid, warps * 32, 0, stream>>>(p); return true;
+    case 2: row_norm_fast_kernel<LPR, V, 2, 0><<<grid, warps * 32, 0, stream>>>(p); return true;
+    case 4: row_norm_fast_kernel<LPR, V, 4, 0><<<grid, warps * 32, 0, stream>>>(p); return true;
   }
   return false;
 }
@@ -181,6 +204,7 @@ int row_norm_launch(const RowNormParams &p, cudaStream_t stream) {
     SIGMA_CHECK_LAUNCH();
     return SIGMA_OK;
   }
+  if (p.mode != 0) { set_error("row_norm: gather / pixel-shuffle modes need D = 4·LPR·V (D=%d has no fast instantiation)", p.D); return SIGMA_EUNSUPPORTED; }
   const int nvec = p.D >> 2;
   const int warps = 8;
   const unsigned grid = (unsigned)((p.rows + warps - 1) / warps);

@@ -177,12 +177,13 @@ def vss_block(blk, x):
 
 def patch_merging(m, x):
     """PatchMerging2D (vmamba.py:619-636)."""
-    H, W = x.shape[1:3]
-    if (W % 2) or (H % 2):
-        x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
-    x = torch.cat([x[:, 0::2, 0::2], x[:, 1::2, 0::2], x[:, 0::2, 1::2], x[:, 1::2, 1::2]], -1)
-    B, H2, W2, C4 = x.shape
-    xn = layernorm(x.view(-1, C4), m.norm)
+    x = x.contiguous()
+    B, H, W, C = x.shape
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    xn = torch.empty((B * H2 * W2, 4 * C), dtype=torch.float32, device=x.device)
+    # 2x2 gather (+ zero padding of odd sizes) + LayerNorm(4C) in one kernel: no concatenated tensor
+    _lib.check(_lib.lib().sigma_patch_merge_norm_fwd(_p(x), _p(m.norm.weight), _p(m.norm.bias), _p(xn), B, H, W, C,
+                                                      float(m.norm.eps), _stream()), "sigma_patch_merge_norm_fwd")
     return linear(xn, m.reduction.weight).view(B, H2, W2, -1)
 
 
@@ -309,9 +310,11 @@ def cvss_decoder_block(blk, x):
 def patch_expand(m, x):
     """PatchExpand (MambaDecoder.py:12-30)."""
     B, H, W, C = x.shape
-    y = linear(x.reshape(B * H * W, C), m.expand.weight).view(B, H, W, 2, 2, C // 2)
-    y = y.permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, C // 2)
-    return ln_nhwc(m.norm, y)
+    y = linear(x.reshape(B * H * W, C), m.expand.weight)             # (B·H·W, 2C) = "b h w (p1 p2 c)"
+    out = torch.empty((B, 2 * H, 2 * W, C // 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().sigma_pixel_shuffle_norm_fwd(_p(y), _p(m.norm.weight), _p(m.norm.bias), _p(out), B, H, W, C // 2,
+                                                        float(m.norm.eps), _stream()), "sigma_pixel_shuffle_norm_fwd")
+    return out
 
 
 def upsample_expand(m, x):

@@ -174,6 +174,45 @@ def test_upsample2x_plain(B, H, W, C):
     assert_close(got, ref.permute(0, 2, 3, 1), 1e-6, 1e-6, "upsample2x plain")
 
 
+@pytest.mark.parametrize("B,H,W,C", [(2, 6, 8, 96), (1, 7, 5, 96), (2, 15, 20, 192), (1, 3, 3, 128), (1, 1, 1, 32)])
+def test_patch_merging_fused(B, H, W, C):
+    """PatchMerging2D (vmamba.py:619-636) incl. odd H / W: gather + LayerNorm kernel + tcgen05 GEMM vs the composed module."""
+    from sigma_b200 import fused, modules as M
+    m = M.PatchMerging2D(C, 2 * C).cuda()
+    with torch.no_grad():
+        for n, prm in m.named_parameters():
+            prm.copy_(P.randn(S, f"pm/{C}/{n}", tuple(prm.shape), 0.2 if prm.dim() > 1 else 0.1, 1.0 if n.endswith("norm.weight") else 0.0))
+        x = P.randn(S, f"pm/x/{B}/{H}/{W}/{C}", (B, H, W, C)).cuda()
+        with M.composed_path():
+            ref = m(x)
+        got = fused.patch_merging(m, x)
+    assert_close(got, ref, 5e-3, 1e-2, "patch_merging (tf32 GEMM)")
+    # the LayerNorm'd gather alone, exactly
+    H2, W2 = (H + 1) // 2, (W + 1) // 2
+    xp = torch.nn.functional.pad(x, (0, 0, 0, W % 2, 0, H % 2))
+    cat = torch.cat([xp[:, 0::2, 0::2], xp[:, 1::2, 0::2], xp[:, 0::2, 1::2], xp[:, 1::2, 1::2]], -1)
+    xn = torch.empty((B * H2 * W2, 4 * C), device="cuda")
+    from sigma_b200 import _lib
+    _lib.check(_lib.lib().sigma_patch_merge_norm_fwd(x.data_ptr(), m.norm.weight.data_ptr(), m.norm.bias.data_ptr(), xn.data_ptr(),
+                                                      B, H, W, C, float(m.norm.eps), torch.cuda.current_stream().cuda_stream), "pm")
+    assert_close(xn.view(B, H2, W2, 4 * C), m.norm(cat), 2e-5, 5e-5, "patch merge gather + LN")
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 3, 5, 192), (1, 15, 20, 384), (1, 2, 2, 768), (1, 1, 3, 256)])
+def test_patch_expand_fused(B, H, W, C):
+    """PatchExpand (MambaDecoder.py:12-30): Linear C->2C, pixel shuffle, LayerNorm(C/2); the shuffle is the store address."""
+    from sigma_b200 import fused, modules as M
+    m = M.PatchExpand((H, W), C).cuda()
+    with torch.no_grad():
+        for n, prm in m.named_parameters():
+            prm.copy_(P.randn(S, f"pe/{C}/{n}", tuple(prm.shape), C ** -0.5 if prm.dim() > 1 else 0.1, 1.0 if n.endswith("norm.weight") else 0.0))
+        x = P.randn(S, f"pe/x/{B}/{H}/{W}/{C}", (B, H, W, C)).cuda()
+        with M.composed_path():
+            ref = m(x)
+        got = fused.patch_expand(m, x)
+    assert_close(got, ref, 5e-3, 8e-3, "patch_expand (tf32 GEMM)")
+
+
 def test_pool_and_scale_add():
     from sigma_b200 import fused
     B, H, W, C = 2, 33, 40, 96
