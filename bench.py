@@ -8,8 +8,9 @@ selective-scan kernel's achieved fraction of the HBM roofline and the reference'
 A "step" is one forward of the whole network over one batch of B images per GPU (weak scaling: every
 rank runs its own B images, no data-path collective — the scan is per-sample).
   value : images/s with the inputs already resident in HBM (CUDA-graph replay, CUDA events, max over ranks)
-  e2e   : the same through the public nn.Module call with HOST (pinned) inputs and logits read back to the
-          host inside the timed region
+  e2e   : the same through the public serving call (sigma_b200.InferencePipeline.submit) with HOST (pinned) inputs
+          and the logits of every step read back to the host, all inside the timed region; copies of neighbouring
+          steps overlap the forward
   roofline / cpu_baseline : see DESIGN.md §Measurement.
 Prints ONE JSON line on rank 0.
 """
@@ -271,23 +272,22 @@ def main():
         torch.cuda.synchronize()
         launches_per_step = _lib.launch_count() - n0
 
-    # ---- CUDA graph of one step
+    # ---- CUDA graph of one step, owned by the serving-side pipeline object (the e2e arm's public call)
+    from sigma_b200.pipeline import InferencePipeline
     graph = None
     static_out = out
-    if not a.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side), torch.no_grad():
-                model(rgb, mx)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph), torch.no_grad():
-                static_out = model(rgb, mx)
-        except Exception as e:  # report, fall back to eager launches (still our kernels)
-            print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
+    pipe = None
+    try:
+        pipe = InferencePipeline(model, B, a.height, a.width, use_graph=not a.no_graph)
+        pipe.rgb.copy_(rgb)
+        pipe.x.copy_(mx)
+        rgb, mx = pipe.rgb, pipe.x                 # the graph's static inputs
+        graph, static_out = pipe.graph, pipe.out
+        del out
+    except Exception as e:  # report, fall back to eager launches (still our kernels)
+        print(f"[bench] pipeline / CUDA graph setup failed ({type(e).__name__}: {e}); running eagerly", file=sys.stderr)
+        pipe, graph = None, None
+        torch.cuda.synchronize()
 
     def step():
         nonlocal static_out
@@ -317,20 +317,41 @@ def main():
     # ---- timed region 2: end to end through the public call, host buffers
     h_rgb = torch.randn(B, 3, a.height, a.width).pin_memory()
     h_mx = torch.randn(B, 3, a.height, a.width).pin_memory()
-    h_out = torch.empty(tuple(static_out.shape), dtype=static_out.dtype).pin_memory()
-    def e2e_step():
-        rgb.copy_(h_rgb, non_blocking=True)
-        mx.copy_(h_mx, non_blocking=True)
-        step()
-        h_out.copy_(static_out, non_blocking=True)
-    for _ in range(3):
-        e2e_step()
-    barrier()
+    h_outs = [torch.empty(tuple(static_out.shape), dtype=static_out.dtype).pin_memory() for _ in range(2)]
+    cur = torch.cuda.current_stream()
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for _ in range(a.steps):
-        e2e_step()
-    s1.record()
+    if pipe is not None:
+        # InferencePipeline: every step copies ITS inputs host->device and ITS logits device->host; the copies of
+        # neighbouring steps overlap the forward (3 streams, double-buffered staging).  Device-timed: the three
+        # streams start after s0 and s1 is recorded after all of them have finished.
+        streams = (pipe.copy_in, pipe.compute, pipe.copy_out)
+        for k in range(3):
+            pipe.submit(h_rgb, h_mx, h_outs[k & 1])
+        pipe.drain()
+        barrier()
+        s0.record(cur)
+        for st in streams:
+            st.wait_event(s0)
+        for k in range(a.steps):
+            pipe.submit(h_rgb, h_mx, h_outs[k & 1])
+        for st in streams:
+            cur.wait_stream(st)
+        s1.record(cur)
+        e2e_mode = "InferencePipeline: H2D / forward / D2H of neighbouring steps overlap (3 streams, double-buffered staging)"
+    else:
+        def e2e_step():
+            rgb.copy_(h_rgb, non_blocking=True)
+            mx.copy_(h_mx, non_blocking=True)
+            step()
+            h_outs[0].copy_(static_out, non_blocking=True)
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        s0.record(cur)
+        for _ in range(a.steps):
+            e2e_step()
+        s1.record(cur)
+        e2e_mode = "serial: H2D, forward, D2H on one stream"
     barrier()
     e2e_ms = dist_util.max_over_ranks(s0.elapsed_time(s1), dev)
     clocks = sampler.stop() if sampler else None
@@ -383,7 +404,7 @@ def main():
                    "l2": "256 MiB flush between timed steps"},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": round(n_img / (e2e_ms * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
-                "d2h_bytes_per_step": out_bytes},
+                "d2h_bytes_per_step": out_bytes, "mode": e2e_mode},
         "gpu_launches": int(launches_per_step) * a.steps,
         "clocks": clocks,
     }
