@@ -401,7 +401,8 @@ def main():
         "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"replicas x{world} (no data-path collective)", "scan_math": "fp32",
                    "dense_math": "tf32 tensor cores (hand-written tcgen05 GEMM), fp32 accumulate" if fused.USE_TCGEN05_GEMM else "tf32 cuBLAS", "cuda_graph": graph is not None,
-                   "l2": "256 MiB flush between timed steps"},
+                   "l2": "256 MiB flush between timed steps",
+                   "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
         "roofline": roofline, "cpu_baseline": cpu,
         "e2e": {"value": round(n_img / (e2e_ms * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "mode": e2e_mode},
