@@ -470,26 +470,26 @@ __global__ void __launch_bounds__(256) upsample2x_plain_kernel(const float *__re
 template <int LPR, int V, int NCLS>
 __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
                                                                         const float *__restrict__ beta, const float *__restrict__ wcls,
-                                                                        float *__restrict__ out, int B, int Hin, int Win, float eps,
-                                                                        int passes) {
-  constexpr int RPW = 32 / LPR, C4 = LPR * V, C = 4 * C4, PPP = 8 * RPW;   // pixels per pass of the 8-warp CTA
+                                                                        float *__restrict__ out, int B, int Hin, int Win, float eps) {
+  constexpr int RPW = 32 / LPR, C4 = LPR * V, C = 4 * C4, PASSES = 32 / RPW;   // a warp owns 32 consecutive output pixels
   __shared__ __align__(16) float sw[NCLS][C];
-  __shared__ float slog[NCLS][PPP];
+  __shared__ float slog[8][NCLS][32];                 // per-warp staging: no CTA barrier in the pixel loop
   for (int i = threadIdx.x; i < NCLS * C; i += blockDim.x) sw[i / C][i % C] = wcls[i];
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
   const int Ho = 2 * Hin, Wo = 2 * Win;
   const long long HWo = (long long)Ho * Wo, npix = (long long)B * HWo;
+  const long long p0 = ((long long)blockIdx.x * 8 + warp) * 32;
+  if (p0 >= npix) return;
   float4 g[V], bt[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     g[v] = __ldg(reinterpret_cast<const float4 *>(gamma) + l + LPR * v);
     bt[v] = __ldg(reinterpret_cast<const float4 *>(beta) + l + LPR * v);
   }
-  for (int pass = 0; pass < passes; ++pass) {
-    const long long p0 = ((long long)blockIdx.x * passes + pass) * PPP;
-    if (p0 >= npix) break;
-    const long long pix = min(p0 + warp * RPW + sub, npix - 1);
+#pragma unroll 1
+  for (int pass = 0; pass < PASSES; ++pass) {
+    const long long pix = min(p0 + pass * RPW + sub, npix - 1);
     const int b = (int)(pix / HWo);
     const int rem = (int)(pix - (long long)b * HWo);
     const int oh = rem / Wo, ow = rem - oh * Wo;
@@ -544,19 +544,16 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
       float a = acc[c];
 #pragma unroll
       for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (l == 0) slog[c][warp * RPW + sub] = a;
+      if (l == 0) slog[warp][c][pass * RPW + sub] = a;
     }
-    __syncthreads();
-    // PPP consecutive pixels x NCLS classes -> NCHW, contiguous runs per class
-    for (int i = threadIdx.x; i < NCLS * PPP; i += blockDim.x) {
-      const int c = i / PPP, j = i % PPP;
-      const long long pp = p0 + j;
-      if (pp < npix) {
-        const long long bb = pp / HWo, r = pp - bb * HWo;
-        out[(bb * NCLS + c) * HWo + r] = slog[c][j];
-      }
-    }
-    __syncthreads();
+  }
+  __syncwarp();
+  // this warp's 32 consecutive pixels x NCLS classes -> NCHW: one 128-byte run per class
+  const long long pp = p0 + lane;
+  if (pp < npix) {
+    const long long bb = pp / HWo, r = pp - bb * HWo;
+#pragma unroll
+    for (int c = 0; c < NCLS; ++c) out[(bb * NCLS + c) * HWo + r] = slog[warp][c][lane];
   }
 }
 
@@ -565,12 +562,10 @@ static bool upsample2x_norm_head_fast(const float *in, const float *gamma, const
                                       int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
   if (NCLS == 0 || NCLS > 24) return false;
   const long long npix = 4LL * B * Hin * Win;
-  const int passes = 8;
 #define TRY(LPR, V)                                                                                                         \
   if (C == 4 * (LPR) * (V)) {                                                                                               \
-    const long long ppc = (long long)passes * 8 * (32 / (LPR));                                                             \
     upsample2x_norm_head_fast_kernel<LPR, V, (NCLS > 0 && NCLS <= 24 ? NCLS : 1)>                                           \
-        <<<(unsigned)((npix + ppc - 1) / ppc), 256, 0, stream>>>(in, gamma, beta, wcls, out, B, Hin, Win, eps, passes);     \
+        <<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(in, gamma, beta, wcls, out, B, Hin, Win, eps);                 \
     return true;                                                                                                            \
   }
   TRY(8, 2) TRY(8, 3) TRY(8, 4) TRY(16, 3) TRY(16, 4)
