@@ -73,16 +73,24 @@ __device__ __forceinline__ float lg2(float x) {
 }
 
 // F.softplus with the default threshold 20 (selective_scan_fwd_kernel.cuh:133,
-// selective_scan_interface.py:107), branch-free so it schedules inside the scan's inner loop:
-//   softplus(x) = max(x,0) + log1p(z),  z = exp(-|x|) in (0,1]
-// log1p(z): 4-term series for z < 2^-6 (rel. err < 1e-8; keeps delta ~ 1e-3..1e-5 accurate, the common
-// case after dt_init), MUFU.LG2 of 1+z otherwise (rel. err < 1e-5 there).  For x > 20, z < 2.1e-9 and the
-// sum rounds to x, which is exactly the reference's thresholded branch.
+// selective_scan_interface.py:107), branch-free and with ONE MUFU op so it schedules inside the scan's inner loop
+// (the SFU is the scan's busiest unit):
+//   softplus(x) = max(x,0) + log1p(z),  z = exp(-|x|) in (0,1],  log1p(z) = z·q(z)
+// q = degree-8 Chebyshev interpolant of log1p(z)/z on [0,1]: relative error of log1p < 2.5e-7 over the whole range
+// evaluated in fp32 (the earlier series / MUFU.LG2 split needed a second MUFU op and reached 1e-5 for z > 2^-6).
+// For x > 20, z < 2.1e-9 and the sum rounds to x, which is exactly the reference's thresholded branch.
 __device__ __forceinline__ float softplus20(float x) {
   const float z = ex2(-fabsf(x) * kLog2e);
-  const float poly = z * fmaf(z, fmaf(z, fmaf(z, -0.25f, 0.33333334f), -0.5f), 1.0f);
-  const float lg = lg2(1.0f + z) * 0.6931471805599453f;
-  return fmaxf(x, 0.f) + (z < 0.015625f ? poly : lg);
+  float q = 0.005126102361828089f;
+  q = fmaf(q, z, -0.029074065387248993f);
+  q = fmaf(q, z, 0.0775160863995552f);
+  q = fmaf(q, z, -0.13602247834205627f);
+  q = fmaf(q, z, 0.19076880812644958f);
+  q = fmaf(q, z, -0.2483539879322052f);
+  q = fmaf(q, z, 0.3331812024116516f);
+  q = fmaf(q, z, -0.4999944567680359f);
+  q = fmaf(q, z, 0.9999999403953552f);
+  return fmaf(q, z, fmaxf(x, 0.f));
 }
 
 // ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2: two fp32 lanes per instruction, same FLOP rate as the

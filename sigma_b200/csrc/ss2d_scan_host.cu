@@ -106,15 +106,7 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   const long long Lseq = kind == SIGMA_DIRS_SEQ2 ? 2LL * H * W : (long long)H * W;
   p.Lseq = Lseq;
   const int LT = lt_for(N);
-  // channels per thread: 2 halves the B/C shared-memory traffic and the address arithmetic per channel (the scan's
-  // co-bottleneck next to the MUFU), 1 doubles the number of warps when batch x K x D is small.
-  const long long warps2 = (long long)batch * ndir * ((D + 63) / 64);
-  int cpt = 1;   // measured (profiles/r01_scan_variants.txt): CPT=2 loses at every Sigma shape up to 32 images/GPU
-  (void)warps2;
-  if (const char *e = getenv("SIGMA_SCAN_CPT")) {
-    const int v = atoi(e);
-    if (v == 1 || v == 2) cpt = v;
-  }
+  const int cpt = 1;   // channels per thread; CPT = 2 (shared B/C reads) lost at every Sigma shape (profiles/r01_scan_variants.txt)
   int maxw = 4;  // warps per CTA (Ss2dCfg::MAXW; the kernels' register budget assumes 128 threads)
   if (const char *e = getenv("SIGMA_SCAN_WARPS")) maxw = std::max(1, std::min(4, atoi(e)));
   const int NW = pick_warps(D, cpt, maxw), DT = 32 * cpt * NW;
@@ -183,13 +175,10 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
     if (const char *e = getenv("SIGMA_SCAN_NST")) p.nst = std::max(2, std::min(Ss2dCfg<16>::MAX_NST, atoi(e)));
   }
   const int nthreads = 32 * NW;
-  switch (N * 8 + cpt) {
-    case 4 * 8 + 1: return dispatch_rp<4, 1>(p, nthreads, stream);
-    case 4 * 8 + 2: return dispatch_rp<4, 2>(p, nthreads, stream);
-    case 8 * 8 + 1: return dispatch_rp<8, 1>(p, nthreads, stream);
-    case 8 * 8 + 2: return dispatch_rp<8, 2>(p, nthreads, stream);
-    case 16 * 8 + 1: return dispatch_rp<16, 1>(p, nthreads, stream);
-    case 16 * 8 + 2: return dispatch_rp<16, 2>(p, nthreads, stream);
+  switch (N) {
+    case 4: return dispatch_rp<4, 1>(p, nthreads, stream);
+    case 8: return dispatch_rp<8, 1>(p, nthreads, stream);
+    case 16: return dispatch_rp<16, 1>(p, nthreads, stream);
   }
   set_error("sigma_ss2d_scan_fwd: d_state=%d unsupported by the fused kernel (4, 8, 16)", N);
   return SIGMA_EUNSUPPORTED;
