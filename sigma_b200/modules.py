@@ -627,7 +627,8 @@ class Backbone_VSSM(VSSM):
         if _fused_ok(x):
             from . import fused
             fused_ln = fused.ln_nhwc
-            x = self.patch_embed[0](x).permute(0, 2, 3, 1)
+            # channels_last input -> cuDNN's NHWC kernel -> the (B,H,W,C) view below is contiguous (no transposing copy)
+            x = self.patch_embed[0](x.contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1)
             x = fused_ln(self.patch_embed[2], x) if isinstance(self.patch_embed[2], nn.LayerNorm) else x.contiguous()
         else:
             x = self.patch_embed(x)
@@ -672,7 +673,15 @@ class RGBXTransformer(nn.Module):
         B = x_rgb.shape[0]
         # Siamese: one weight set, both streams in one 2B batch (the reference runs them back to back,
         # dual_vmamba.py:85-86; LayerNorm-only network, so batching is exact)
-        outs = self.vssm.forward_nhwc(torch.cat([x_rgb, x_e], dim=0))
+        if _fused_ok(x_rgb):
+            # the 2B batch is assembled directly in channels_last memory (what the patch-embed conv wants)
+            x2 = torch.empty((2 * B,) + tuple(x_rgb.shape[1:]), dtype=x_rgb.dtype, device=x_rgb.device,
+                             memory_format=torch.channels_last)
+            x2[:B].copy_(x_rgb)
+            x2[B:].copy_(x_e)
+        else:
+            x2 = torch.cat([x_rgb, x_e], dim=0)
+        outs = self.vssm.forward_nhwc(x2)
         fused = []
         for i in range(4):
             o_r, o_x = outs[i][:B], outs[i][B:]
