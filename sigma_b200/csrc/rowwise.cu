@@ -90,7 +90,8 @@ __global__ void __launch_bounds__(256) row_norm_fast_kernel(const RowNormParams 
   const long long row_raw = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + sub;
   const bool valid = row_raw < p.rows;
   const long long row = valid ? row_raw : p.rows - 1;     // keep the warp convergent for the shuffles
-  const long long bi = row / p.rows_per_batch, ri = row - bi * p.rows_per_batch;
+  long long bi = 0, ri = row;
+  if (p.rows_per_batch < p.rows) { bi = row / p.rows_per_batch; ri = row - bi * p.rows_per_batch; }   // 64-bit division only when batched
   const float4 *in = reinterpret_cast<const float4 *>(p.y + bi * p.in_batch_stride + ri * p.D);
   const long long ks4 = p.k_stride >> 2;
   float4 x[V], kk[K > 1 ? (K - 1) * V : 1], zz[V];
@@ -439,27 +440,27 @@ __global__ void __launch_bounds__(256) upsample2x_norm_kernel(const float *__res
 // ---- plain bilinear x2 (no norm), channels-last: one thread per (output pixel, 4 channels) ----
 __global__ void __launch_bounds__(256) upsample2x_plain_kernel(const float *__restrict__ in, float *__restrict__ out, int B,
                                                               int Hin, int Win, int C) {
-  const int nvec = C >> 2, Ho = 2 * Hin, Wo = 2 * Win;
-  const long long total = (long long)B * Ho * Wo * nvec;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % nvec);
-    const long long pix = i / nvec;
-    const int b = (int)(pix / ((long long)Ho * Wo));
-    const int rem = (int)(pix - (long long)b * Ho * Wo);
-    const int oh = rem / Wo, ow = rem - oh * Wo;
+  // thread = (output pixel, 4 channels); grid.y = image, so all index math is 32-bit (no 64-bit divisions)
+  const unsigned nvec = C >> 2, Ho = 2 * Hin, Wo = 2 * Win, per_img = Ho * Wo * nvec;
+  const int b = blockIdx.y;
+  const float4 *src = reinterpret_cast<const float4 *>(in) + (long long)b * Hin * Win * nvec;
+  float4 *dst = reinterpret_cast<float4 *>(out) + (long long)b * per_img;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+    const unsigned pix = i / nvec, q = i - pix * nvec;
+    const unsigned oh = pix / Wo, ow = pix - oh * Wo;
     int h0, h1, w0, w1;
     float fh, fw;
-    bilinear2x_taps(oh, Hin, h0, h1, fh);
-    bilinear2x_taps(ow, Win, w0, w1, fw);
-    const float4 *base = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C) + q;
-    const float4 a = __ldg(base + ((long long)h0 * Win + w0) * nvec), bq = __ldg(base + ((long long)h0 * Win + w1) * nvec);
-    const float4 c = __ldg(base + ((long long)h1 * Win + w0) * nvec), d = __ldg(base + ((long long)h1 * Win + w1) * nvec);
+    bilinear2x_taps((int)oh, Hin, h0, h1, fh);
+    bilinear2x_taps((int)ow, Win, w0, w1, fw);
+    const float4 *base = src + q;
+    const float4 a = __ldg(base + (unsigned)(h0 * Win + w0) * nvec), bq = __ldg(base + (unsigned)(h0 * Win + w1) * nvec);
+    const float4 c = __ldg(base + (unsigned)(h1 * Win + w0) * nvec), d = __ldg(base + (unsigned)(h1 * Win + w1) * nvec);
     float4 o;   // same association as PyTorch's upsample_bilinear2d
     o.x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
     o.y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
     o.z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
     o.w = (1.f - fh) * ((1.f - fw) * a.w + fw * bq.w) + fh * ((1.f - fw) * c.w + fw * d.w);
-    reinterpret_cast<float4 *>(out)[i] = o;
+    dst[i] = o;
   }
 }
 
@@ -481,6 +482,10 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
   const long long HWo = (long long)Ho * Wo, npix = (long long)B * HWo;
   const long long p0 = ((long long)blockIdx.x * 8 + warp) * 32;
   if (p0 >= npix) return;
+  // (image, row, column) of the warp's first pixel by division ONCE; the 32 pixels are consecutive, so each pass
+  // advances the coordinates (64-bit divisions per pass were the hidden cost of the first version)
+  const int b0 = (int)(p0 / HWo);
+  const int rem0 = (int)(p0 - (long long)b0 * HWo), oh0 = rem0 / Wo, ow0 = rem0 - oh0 * Wo;
   float4 g[V], bt[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -489,10 +494,10 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
   }
 #pragma unroll 1
   for (int pass = 0; pass < PASSES; ++pass) {
-    const long long pix = min(p0 + pass * RPW + sub, npix - 1);
-    const int b = (int)(pix / HWo);
-    const int rem = (int)(pix - (long long)b * HWo);
-    const int oh = rem / Wo, ow = rem - oh * Wo;
+    int b = b0, oh = oh0, ow = ow0 + pass * RPW + sub;
+    while (ow >= Wo) { ow -= Wo; ++oh; }
+    while (oh >= Ho) { oh -= Ho; ++b; }
+    if (b >= B) { b = B - 1; oh = Ho - 1; ow = Wo - 1; }      // past the end: recompute the last pixel (never stored)
     int h0, h1, w0, w1;
     float fh, fw;
     bilinear2x_taps(oh, Hin, h0, h1, fh);
@@ -551,7 +556,8 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
   // this warp's 32 consecutive pixels x NCLS classes -> NCHW: one 128-byte run per class
   const long long pp = p0 + lane;
   if (pp < npix) {
-    const long long bb = pp / HWo, r = pp - bb * HWo;
+    long long bb = b0, r = (long long)rem0 + lane;
+    while (r >= HWo) { r -= HWo; ++bb; }
 #pragma unroll
     for (int c = 0; c < NCLS; ++c) out[(bb * NCLS + c) * HWo + r] = slog[warp][c][lane];
   }
@@ -578,8 +584,9 @@ static int upsample2x_norm_dispatch(const float *in, const float *gamma, const f
                                     int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
   const long long npix = 4LL * B * Hin * Win;
   if (NCLS == 0 && gamma == nullptr) {   // plain bilinear x2
-    const long long total = npix * (C >> 2);
-    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148LL * 32);
+    const long long per_img = 4LL * Hin * Win * (C >> 2);
+    if (per_img >= (1LL << 31)) { set_error("upsample2x: image too large for 32-bit indexing"); return SIGMA_EUNSUPPORTED; }
+    dim3 grid((unsigned)std::min<long long>((per_img + 255) / 256, 148LL * 8), (unsigned)B);
     upsample2x_plain_kernel<<<grid, 256, 0, stream>>>(in, out, B, Hin, Win, C);
     SIGMA_CHECK_LAUNCH();
     return SIGMA_OK;
