@@ -188,6 +188,18 @@ int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const f
 int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *bias, const float *residual, int64_t ldr,
                       const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * SURVEY.md §8(f) rank 2, first piece: the evaluator's per-batch metric on the device (eval.py:22-29,
+ * utils/metric.py:8-15).  pred = argmax over classes of logits (batch, classes, H, W) — the index numpy.argmax
+ * returns for exp(score) (evaluator.py:520,449); for labels in [0, classes): hist[label·classes + pred] += 1,
+ * counts[0] (labeled) += 1, counts[1] (correct) += (pred == label).  hist (classes²) and counts (2) are uint64
+ * ACCUMULATORS in device memory (zero them once per evaluation); labels (batch, H, W) are uint8 / int32 / int64
+ * (label_bytes = 1 / 4 / 8), anything outside [0, classes) — e.g. 255 — is ignored; pred (batch·H·W uint8) may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int sigma_argmax_hist_fwd(const float *logits, const void *labels, int label_bytes, uint64_t *hist,
+                          uint64_t *counts, uint8_t *pred, int batch, int num_classes, int64_t HW,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

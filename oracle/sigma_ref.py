@@ -256,6 +256,25 @@ def encoder_decoder(rgb, mx, sd):
     return F.interpolate(out, size=rgb.shape[2:], mode="bilinear", align_corners=False)
 
 
+def hist_info(n_cl, pred, gt):
+    """utils/metric.py:8-15 restated: confusion matrix (rows = ground truth, columns = prediction) over the pixels whose
+    label is in [0, n_cl), the number of such pixels, and the number of correct ones."""
+    pred, gt = np.asarray(pred), np.asarray(gt)
+    k = (gt >= 0) & (gt < n_cl)
+    hist = np.bincount(n_cl * gt[k].astype(np.int64) + pred[k].astype(np.int64), minlength=n_cl ** 2).reshape(n_cl, n_cl)
+    return hist, int(k.sum()), int((pred[k] == gt[k]).sum())
+
+
+def compute_score(hist, correct, labeled):
+    """utils/metric.py:17-33 restated: per-class IoU, mIoU, frequency-weighted IoU, mean class accuracy, pixel accuracy."""
+    hist = np.asarray(hist, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        iou = np.diag(hist) / (hist.sum(1) + hist.sum(0) - np.diag(hist))
+        freq = hist.sum(1) / hist.sum()
+        class_acc = np.diag(hist) / hist.sum(axis=1)
+        return iou, float(np.nanmean(iou)), float((iou[freq > 0] * freq[freq > 0]).sum()), float(np.nanmean(class_acc)), correct / labeled
+
+
 def mean_iou(pred, gt, n_cl):
     """utils/metric.py:8-29 (hist_info + compute_score), returns (iou per class, mIoU)."""
     k = (gt >= 0) & (gt < n_cl)

@@ -200,6 +200,8 @@ int sigma_scan_fwd_f32_split(const float *u, const float *delta, const float *A,
 // ---------------------------------------------------------------------------------------------
 namespace sigma {
 int row_norm_launch(const RowNormParams &p, cudaStream_t stream);
+int argmax_hist_launch(const float *logits, const void *labels, int label_bytes, unsigned long long *hist,
+                       unsigned long long *counts, unsigned char *pred_out, int batch, int ncls, long long HW, cudaStream_t stream);
 int dwconv3x3_silu_launch(const float *x, long long x_row_stride, long long x_batch_stride, const float *w,
                           const float *bias, float *y, long long y_batch_stride, int batch, int H, int W, int D,
                           cudaStream_t stream);
@@ -340,6 +342,14 @@ int sigma_upsample2x_norm_head_fwd(const float *x, const float *w, const float *
                   "sigma_upsample2x_norm_head_fwd: bad sizes");
   SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(wcls), "sigma_upsample2x_norm_head_fwd: pointers must be 16-byte aligned");
   return upsample2x_norm_launch(x, w, b, wcls, num_classes, logits, batch, H, W, C, eps, (cudaStream_t)stream);
+}
+
+int sigma_argmax_hist_fwd(const float *logits, const void *labels, int label_bytes, uint64_t *hist, uint64_t *counts,
+                          uint8_t *pred, int batch, int num_classes, int64_t HW, void *stream) {
+  SIGMA_CHECK_ARG(logits && labels && hist && counts, "sigma_argmax_hist_fwd: null pointer");
+  SIGMA_CHECK_ARG(batch > 0 && HW > 0 && num_classes > 0 && num_classes <= 255, "sigma_argmax_hist_fwd: bad sizes (1 <= classes <= 255)");
+  return argmax_hist_launch(logits, labels, label_bytes, (unsigned long long *)hist, (unsigned long long *)counts, pred, batch,
+                            num_classes, HW, (cudaStream_t)stream);
 }
 
 int sigma_pool_avgmax_partial_fwd(const float *x, float *partial, int batch, int64_t L, int C, int nslice, void *stream) {
