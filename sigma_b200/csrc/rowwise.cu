@@ -472,7 +472,10 @@ template <int LPR, int V, int NCLS>
 __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
                                                                         const float *__restrict__ beta, const float *__restrict__ wcls,
                                                                         float *__restrict__ out, int B, int Hin, int Win, float eps) {
-  constexpr int RPW = 32 / LPR, C4 = LPR * V, C = 4 * C4, PASSES = 32 / RPW;   // a warp owns 32 consecutive output pixels
+  // PX pixels per lane group and pass: every classifier-weight LDS.128 (4 shared-memory wavefronts: the 4 lane
+  // groups of a warp read the same 128 bytes in different quarter-warps) then feeds PX pixels.  With PX = 1 the kernel
+  // was bound by those wavefronts (27 x 4 per 4 pixels; 5.2 ms for 74 x 480 x 640 pixels).
+  constexpr int RPW = 32 / LPR, PX = 2, C4 = LPR * V, C = 4 * C4, PASSES = 32 / (RPW * PX);   // a warp owns 32 consecutive pixels
   __shared__ __align__(16) float sw[NCLS][C];
   __shared__ float slog[8][NCLS][32];                 // per-warp staging: no CTA barrier in the pixel loop
   for (int i = threadIdx.x; i < NCLS * C; i += blockDim.x) sw[i / C][i % C] = wcls[i];
@@ -483,7 +486,7 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
   const long long p0 = ((long long)blockIdx.x * 8 + warp) * 32;
   if (p0 >= npix) return;
   // (image, row, column) of the warp's first pixel by division ONCE; the 32 pixels are consecutive, so each pass
-  // advances the coordinates (64-bit divisions per pass were the hidden cost of the first version)
+  // advances the coordinates
   const int b0 = (int)(p0 / HWo);
   const int rem0 = (int)(p0 - (long long)b0 * HWo), oh0 = rem0 / Wo, ow0 = rem0 - oh0 * Wo;
   float4 g[V], bt[V];
@@ -494,63 +497,77 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
   }
 #pragma unroll 1
   for (int pass = 0; pass < PASSES; ++pass) {
-    int b = b0, oh = oh0, ow = ow0 + pass * RPW + sub;
-    while (ow >= Wo) { ow -= Wo; ++oh; }
-    while (oh >= Ho) { oh -= Ho; ++b; }
-    if (b >= B) { b = B - 1; oh = Ho - 1; ow = Wo - 1; }      // past the end: recompute the last pixel (never stored)
-    int h0, h1, w0, w1;
-    float fh, fw;
-    bilinear2x_taps(oh, Hin, h0, h1, fh);
-    bilinear2x_taps(ow, Win, w0, w1, fw);
-    const float4 *base = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C) + l;
-    const float4 *r00 = base + ((long long)h0 * Win + w0) * C4, *r01 = base + ((long long)h0 * Win + w1) * C4;
-    const float4 *r10 = base + ((long long)h1 * Win + w0) * C4, *r11 = base + ((long long)h1 * Win + w1) * C4;
-    float4 x[V];
-    float s = 0.f;
+    float4 x[PX][V];
+    float mean[PX], rstd[PX];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const float4 a = __ldg(r00 + LPR * v), bq = __ldg(r01 + LPR * v), c = __ldg(r10 + LPR * v), d = __ldg(r11 + LPR * v);
-      x[v].x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
-      x[v].y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
-      x[v].z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
-      x[v].w = (1.f - fh) * ((1.f - fw) * a.w + fw * bq.w) + fh * ((1.f - fw) * c.w + fw * d.w);
-      s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+    for (int px = 0; px < PX; ++px) {
+      // pixel (pass, px, sub) of the warp's 32: index pass*PX*RPW + px*RPW + sub
+      int b = b0, oh = oh0, ow = ow0 + (pass * PX + px) * RPW + sub;
+      while (ow >= Wo) { ow -= Wo; ++oh; }
+      while (oh >= Ho) { oh -= Ho; ++b; }
+      if (b >= B) { b = B - 1; oh = Ho - 1; ow = Wo - 1; }      // past the end: recompute the last pixel (never stored)
+      int h0, h1, w0, w1;
+      float fh, fw;
+      bilinear2x_taps(oh, Hin, h0, h1, fh);
+      bilinear2x_taps(ow, Win, w0, w1, fw);
+      const float4 *base = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C) + l;
+      const float4 *r00 = base + ((long long)h0 * Win + w0) * C4, *r01 = base + ((long long)h0 * Win + w1) * C4;
+      const float4 *r10 = base + ((long long)h1 * Win + w0) * C4, *r11 = base + ((long long)h1 * Win + w1) * C4;
+      float s = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float4 a = __ldg(r00 + LPR * v), bq = __ldg(r01 + LPR * v), c = __ldg(r10 + LPR * v), d = __ldg(r11 + LPR * v);
+        x[px][v].x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
+        x[px][v].y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
+        x[px][v].z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
+        x[px][v].w = (1.f - fh) * ((1.f - fw) * a.w + fw * bq.w) + fh * ((1.f - fw) * c.w + fw * d.w);
+        s += (x[px][v].x + x[px][v].y) + (x[px][v].z + x[px][v].w);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean[px] = s / (float)C;
+      float q = 0.f;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const float dx = x[px][v].x - mean[px], dy = x[px][v].y - mean[px], dz = x[px][v].z - mean[px], dw = x[px][v].w - mean[px];
+        q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      rstd[px] = rsqrtf(q / (float)C + eps);
     }
+    float acc[PX][NCLS];
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)C;
-    float q = 0.f;
+    for (int px = 0; px < PX; ++px)
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const float dx = x[v].x - mean, dy = x[v].y - mean, dz = x[v].z - mean, dw = x[v].w - mean;
-      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-    }
-#pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)C + eps);
-    float acc[NCLS];
-#pragma unroll
-    for (int c = 0; c < NCLS; ++c) acc[c] = 0.f;
+      for (int c = 0; c < NCLS; ++c) acc[px][c] = 0.f;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      float4 o;
-      o.x = fmaf((x[v].x - mean) * rstd, g[v].x, bt[v].x);
-      o.y = fmaf((x[v].y - mean) * rstd, g[v].y, bt[v].y);
-      o.z = fmaf((x[v].z - mean) * rstd, g[v].z, bt[v].z);
-      o.w = fmaf((x[v].w - mean) * rstd, g[v].w, bt[v].w);
+      float4 o[PX];
+#pragma unroll
+      for (int px = 0; px < PX; ++px) {
+        o[px].x = fmaf((x[px][v].x - mean[px]) * rstd[px], g[v].x, bt[v].x);
+        o[px].y = fmaf((x[px][v].y - mean[px]) * rstd[px], g[v].y, bt[v].y);
+        o[px].z = fmaf((x[px][v].z - mean[px]) * rstd[px], g[v].z, bt[v].z);
+        o[px].w = fmaf((x[px][v].w - mean[px]) * rstd[px], g[v].w, bt[v].w);
+      }
 #pragma unroll
       for (int c = 0; c < NCLS; ++c) {
         const float4 wv = *reinterpret_cast<const float4 *>(&sw[c][4 * (l + LPR * v)]);
-        acc[c] = fmaf(o.x, wv.x, fmaf(o.y, wv.y, fmaf(o.z, wv.z, fmaf(o.w, wv.w, acc[c]))));
+#pragma unroll
+        for (int px = 0; px < PX; ++px)
+          acc[px][c] = fmaf(o[px].x, wv.x, fmaf(o[px].y, wv.y, fmaf(o[px].z, wv.z, fmaf(o[px].w, wv.w, acc[px][c]))));
       }
     }
 #pragma unroll
-    for (int c = 0; c < NCLS; ++c) {
-      float a = acc[c];
+    for (int px = 0; px < PX; ++px)
 #pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-      if (l == 0) slog[warp][c][pass * RPW + sub] = a;
-    }
+      for (int c = 0; c < NCLS; ++c) {
+        float a = acc[px][c];
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (l == 0) slog[warp][c][(pass * PX + px) * RPW + sub] = a;
+      }
   }
   __syncwarp();
   // this warp's 32 consecutive pixels x NCLS classes -> NCHW: one 128-byte run per class
