@@ -468,55 +468,62 @@ __global__ void __launch_bounds__(256) upsample2x_plain_kernel(const float *__re
 // (LPR lanes per pixel, V float4 per lane), so LayerNorm and the NCLS dot products reduce with log2(LPR) shuffles
 // for 32/LPR pixels instead of 5 per pixel; the head weights are read from shared memory (LDS.128, 128-byte rows).
 // The generic kernel above spends 55 warp shuffles per pixel: 5 ms for 32 x 480 x 640 pixels. ----
+// CTA = an 8 x 32 tile of OUTPUT pixels.  Its (8/2 + 2) x (32/2 + 2) input pixels are staged ONCE in shared memory:
+// bilinear x2 reads every input pixel for 16 (tap, output pixel) pairs, and with the taps read from global memory
+// the kernel was bound by L2 -> L1 traffic (~17 GB for 74 images; 5.0 ms).  Warp w owns output row w of the tile:
+// 32 consecutive pixels, 32/LPR x PX = 8 per pass.
+constexpr int UH_TH = 8, UH_TW = 32, UH_IH = UH_TH / 2 + 2, UH_IW = UH_TW / 2 + 2;
+
 template <int LPR, int V, int NCLS>
 __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const float *__restrict__ in, const float *__restrict__ gamma,
                                                                         const float *__restrict__ beta, const float *__restrict__ wcls,
                                                                         float *__restrict__ out, int B, int Hin, int Win, float eps) {
-  // PX pixels per lane group and pass: every classifier-weight LDS.128 (4 shared-memory wavefronts: the 4 lane
-  // groups of a warp read the same 128 bytes in different quarter-warps) then feeds PX pixels.  With PX = 1 the kernel
-  // was bound by those wavefronts (27 x 4 per 4 pixels; 5.2 ms for 74 x 480 x 640 pixels).
-  constexpr int RPW = 32 / LPR, PX = 2, C4 = LPR * V, C = 4 * C4, PASSES = 32 / (RPW * PX);   // a warp owns 32 consecutive pixels
-  __shared__ __align__(16) float sw[NCLS][C];
-  __shared__ float slog[8][NCLS][32];                 // per-warp staging: no CTA barrier in the pixel loop
-  for (int i = threadIdx.x; i < NCLS * C; i += blockDim.x) sw[i / C][i % C] = wcls[i];
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
+  constexpr int RPW = 32 / LPR, PX = 2, C4 = LPR * V, C = 4 * C4, PASSES = 32 / (RPW * PX);
+  extern __shared__ __align__(16) float smem_uh[];
+  float4 *tile = reinterpret_cast<float4 *>(smem_uh);                         // [UH_IH][UH_IW][C4]
+  float *sw = smem_uh + UH_IH * UH_IW * C;                                    // [NCLS][C]
+  float *slog = sw + NCLS * C;                                                // [8][NCLS][32]
   const int Ho = 2 * Hin, Wo = 2 * Win;
-  const long long HWo = (long long)Ho * Wo, npix = (long long)B * HWo;
-  const long long p0 = ((long long)blockIdx.x * 8 + warp) * 32;
-  if (p0 >= npix) return;
-  // (image, row, column) of the warp's first pixel by division ONCE; the 32 pixels are consecutive, so each pass
-  // advances the coordinates
-  const int b0 = (int)(p0 / HWo);
-  const int rem0 = (int)(p0 - (long long)b0 * HWo), oh0 = rem0 / Wo, ow0 = rem0 - oh0 * Wo;
+  const int b = blockIdx.z, oh_t = blockIdx.y * UH_TH, ow_t = blockIdx.x * UH_TW;
+  const int i0 = oh_t / 2 - 1, j0 = ow_t / 2 - 1;                             // input coordinates of tile[0][0]
+  const float4 *src = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C);
+  for (int i = threadIdx.x; i < UH_IH * UH_IW * C4; i += blockDim.x) {
+    const int pix = i / C4, q = i - pix * C4, ri = pix / UH_IW, ci = pix - ri * UH_IW;
+    const int hh = min(max(i0 + ri, 0), Hin - 1), ww = min(max(j0 + ci, 0), Win - 1);   // edge replicate = the taps' clamping
+    tile[i] = __ldg(src + ((long long)hh * Win + ww) * C4 + q);
+  }
+  for (int i = threadIdx.x; i < NCLS * C; i += blockDim.x) sw[i] = wcls[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
+  const int oh = oh_t + warp;
+  if (oh >= Ho) return;                                                        // warp-uniform; no CTA barrier below
+  int h0, h1;
+  float fh;
+  bilinear2x_taps(oh, Hin, h0, h1, fh);
+  const float4 *row0 = tile + (h0 - i0) * UH_IW * C4 + l, *row1 = tile + (h1 - i0) * UH_IW * C4 + l;
   float4 g[V], bt[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     g[v] = __ldg(reinterpret_cast<const float4 *>(gamma) + l + LPR * v);
     bt[v] = __ldg(reinterpret_cast<const float4 *>(beta) + l + LPR * v);
   }
+  float *mylog = slog + warp * NCLS * 32;
 #pragma unroll 1
   for (int pass = 0; pass < PASSES; ++pass) {
     float4 x[PX][V];
     float mean[PX], rstd[PX];
 #pragma unroll
     for (int px = 0; px < PX; ++px) {
-      // pixel (pass, px, sub) of the warp's 32: index pass*PX*RPW + px*RPW + sub
-      int b = b0, oh = oh0, ow = ow0 + (pass * PX + px) * RPW + sub;
-      while (ow >= Wo) { ow -= Wo; ++oh; }
-      while (oh >= Ho) { oh -= Ho; ++b; }
-      if (b >= B) { b = B - 1; oh = Ho - 1; ow = Wo - 1; }      // past the end: recompute the last pixel (never stored)
-      int h0, h1, w0, w1;
-      float fh, fw;
-      bilinear2x_taps(oh, Hin, h0, h1, fh);
+      const int ow = min(ow_t + (pass * PX + px) * RPW + sub, Wo - 1);         // past the right edge: recompute the last column
+      int w0, w1;
+      float fw;
       bilinear2x_taps(ow, Win, w0, w1, fw);
-      const float4 *base = reinterpret_cast<const float4 *>(in + (long long)b * Hin * Win * C) + l;
-      const float4 *r00 = base + ((long long)h0 * Win + w0) * C4, *r01 = base + ((long long)h0 * Win + w1) * C4;
-      const float4 *r10 = base + ((long long)h1 * Win + w0) * C4, *r11 = base + ((long long)h1 * Win + w1) * C4;
+      const int c0 = (w0 - j0) * C4, c1 = (w1 - j0) * C4;
       float s = 0.f;
 #pragma unroll
       for (int v = 0; v < V; ++v) {
-        const float4 a = __ldg(r00 + LPR * v), bq = __ldg(r01 + LPR * v), c = __ldg(r10 + LPR * v), d = __ldg(r11 + LPR * v);
+        const float4 a = row0[c0 + LPR * v], bq = row0[c1 + LPR * v], c = row1[c0 + LPR * v], d = row1[c1 + LPR * v];
         x[px][v].x = (1.f - fh) * ((1.f - fw) * a.x + fw * bq.x) + fh * ((1.f - fw) * c.x + fw * d.x);
         x[px][v].y = (1.f - fh) * ((1.f - fw) * a.y + fw * bq.y) + fh * ((1.f - fw) * c.y + fw * d.y);
         x[px][v].z = (1.f - fh) * ((1.f - fw) * a.z + fw * bq.z) + fh * ((1.f - fw) * c.z + fw * d.z);
@@ -553,7 +560,7 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
       }
 #pragma unroll
       for (int c = 0; c < NCLS; ++c) {
-        const float4 wv = *reinterpret_cast<const float4 *>(&sw[c][4 * (l + LPR * v)]);
+        const float4 wv = *reinterpret_cast<const float4 *>(&sw[c * C + 4 * (l + LPR * v)]);
 #pragma unroll
         for (int px = 0; px < PX; ++px)
           acc[px][c] = fmaf(o[px].x, wv.x, fmaf(o[px].y, wv.y, fmaf(o[px].z, wv.z, fmaf(o[px].w, wv.w, acc[px][c]))));
@@ -566,17 +573,16 @@ __global__ void __launch_bounds__(256) upsample2x_norm_head_fast_kernel(const fl
         float a = acc[px][c];
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (l == 0) slog[warp][c][(pass * PX + px) * RPW + sub] = a;
+        if (l == 0) mylog[c * 32 + (pass * PX + px) * RPW + sub] = a;
       }
   }
   __syncwarp();
-  // this warp's 32 consecutive pixels x NCLS classes -> NCHW: one 128-byte run per class
-  const long long pp = p0 + lane;
-  if (pp < npix) {
-    long long bb = b0, r = (long long)rem0 + lane;
-    while (r >= HWo) { r -= HWo; ++bb; }
+  // this warp's 32 consecutive pixels of output row oh x NCLS classes -> NCHW: one 128-byte run per class
+  const int ow = ow_t + lane;
+  if (ow < Wo) {
+    float *op = out + ((long long)b * NCLS * Ho + oh) * Wo + ow;
 #pragma unroll
-    for (int c = 0; c < NCLS; ++c) out[(bb * NCLS + c) * HWo + r] = slog[warp][c][lane];
+    for (int c = 0; c < NCLS; ++c) op[(long long)c * Ho * Wo] = mylog[c * 32 + lane];
   }
 }
 
@@ -585,10 +591,16 @@ static bool upsample2x_norm_head_fast(const float *in, const float *gamma, const
                                       int B, int Hin, int Win, int C, float eps, cudaStream_t stream) {
   if (NCLS == 0 || NCLS > 24) return false;
   const long long npix = 4LL * B * Hin * Win;
+  (void)npix;
+  if (B > 65535 || (2 * Hin + UH_TH - 1) / UH_TH > 65535) return false;
 #define TRY(LPR, V)                                                                                                         \
   if (C == 4 * (LPR) * (V)) {                                                                                               \
-    upsample2x_norm_head_fast_kernel<LPR, V, (NCLS > 0 && NCLS <= 24 ? NCLS : 1)>                                           \
-        <<<(unsigned)((npix + 255) / 256), 256, 0, stream>>>(in, gamma, beta, wcls, out, B, Hin, Win, eps);                 \
+    constexpr int NC = (NCLS > 0 && NCLS <= 24 ? NCLS : 1);                                                                 \
+    auto kern = upsample2x_norm_head_fast_kernel<LPR, V, NC>;                                                               \
+    const size_t smem = sizeof(float) * ((size_t)UH_IH * UH_IW * C + (size_t)NC * C + 8 * NC * 32);                         \
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;    \
+    dim3 grid((2 * Win + UH_TW - 1) / UH_TW, (2 * Hin + UH_TH - 1) / UH_TH, B);                                             \
+    kern<<<grid, 256, smem, stream>>>(in, gamma, beta, wcls, out, B, Hin, Win, eps);                                        \
     return true;                                                                                                            \
   }
   TRY(8, 2) TRY(8, 3) TRY(8, 4) TRY(16, 3) TRY(16, 4)
