@@ -7,26 +7,24 @@
 //   softplus -> selective scan (state in registers, one MUFU.EX2 per element) -> D skip -> store at the
 //   POSITION the value belongs to (so CrossMerge's un-flip / un-transpose disappear).
 //
-// Mapping: one thread owns CPT (1 or 2) channels with all N states of each in registers; a warp covers 32
-// consecutive channels (and the 32 that lie DT/2 further for CPT = 2), so every global / shared access of a warp
-// is a 128-byte row and B / C / dt_r are broadcast shared reads shared by the thread's channels.  No shuffles.
-// The recurrence runs on packed fp32x2 instructions (FFMA2 / FMUL2 over state pairs): per (channel, position)
-// and state pair FMUL2 + 2 MUFU.EX2 + FMUL2 + FFMA2 + FFMA2, i.e. 3 issue slots per element instead of 5.
-// History (profiles/r01_scan_variants.txt): 4 lanes/channel was issue-bound; 1 thread/channel with scalar
-// fp32 left MUFU, the LDS return path (2N floats of B/C per channel-position) and issue each ~50 % busy;
-// CPT = 2 halves the B/C traffic per channel and FFMA2 halves the fp32 issue slots.
+// Mapping: one thread owns one channel (CPT = 1; the template keeps a 2-channel variant that shares the B / C reads
+// and lost at every measured shape, not instantiated) with all N states in registers; a warp covers 32 consecutive
+// channels, so every global / shared access of a warp is a 128-byte row and B / C / dt_r are broadcast shared reads.
+// No shuffles.  The recurrence runs on packed fp32x2 instructions (FFMA2 / FMUL2 over state pairs): per (channel,
+// position) and state pair FMUL2 + 2 MUFU.EX2 + FMUL2 + FFMA2 + FFMA2, i.e. 3 issue slots per element instead of 5.
+// History (profiles/r01_scan_variants.txt): 4 lanes/channel was issue-bound; 1 thread/channel with scalar fp32 left
+// MUFU, the LDS return path and issue each ~50 % busy; the current version runs the MUFU pipe at 75 % of peak.
 // CTA = (channel tile DT, direction k [x L-segment], image b) = DT/32 warps, all computing.
-// Tiles of LT scan positions are staged HBM -> shared by TMA (cp.async.bulk.tensor) through an NST-deep ring
-// (no CTA-wide barrier in the loop): a "full" mbarrier per slot signals TMA completion; a per-slot arrival counter
-// replaces the usual "empty" barrier — the warp whose arrival completes a round (the LAST warp to finish the tile)
-// immediately requests the tile that reuses the slot, so nobody ever waits for a slot and a tile is requested
-// NST-1 tiles ahead of its first use.  An earlier version had a dedicated producer warp; it cost a fifth of the
-// register file (12 instead of 16 scanning warps per SM at 128 registers).  Waits on "full" are non-suspending
-// spins (test_wait): a suspended try_wait costs a microsecond-scale wake-up.
-// y goes straight from registers to HBM (a warp writes 32 consecutive channels of one position = one
-// 128-byte row).
-// Per group of 4 positions the delta' of the NEXT group is computed while the recurrence of the current one
-// runs (software pipelining: the only serial dependency is the fma h = a·h + b).
+// Tiles of LT scan positions are staged HBM -> shared by TMA (cp.async.bulk.tensor) through a ring whose depth the
+// host chooses (no CTA-wide barrier in the loop): a "full" mbarrier per slot signals TMA completion; a per-slot
+// arrival counter replaces the usual "empty" barrier — the warp whose arrival completes a round (the LAST warp to
+// finish the tile) immediately requests the tile that reuses the slot, so nobody ever waits for a slot and a tile
+// is requested depth-1 tiles ahead of its first use.  An earlier version had a dedicated producer warp (a fifth of
+// the CTA's registers).  Waits on "full" are non-suspending spins (test_wait): a suspended try_wait costs a
+// microsecond-scale wake-up.
+// y goes straight from registers to HBM (a warp writes 32 consecutive channels of one position = one 128-byte row).
+// Per group of G positions the delta' of the NEXT group is computed in the same basic block as the recurrence of
+// the current one (software pipelining across tile boundaries: the only serial dependency is h = a·h + b).
 #pragma once
 #include "scan_core.cuh"
 #include "tma.cuh"

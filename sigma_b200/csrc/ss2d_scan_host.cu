@@ -76,7 +76,7 @@ static int dispatch_rp(const Ss2dParams &p, int nthreads, cudaStream_t s) {
 static int kind_dirs(int kind) { return kind == SIGMA_DIRS_CROSS4 ? 4 : (kind == SIGMA_DIRS_SEQ2 ? 2 : 1); }
 static int lt_for(int N) { return N >= 16 ? Ss2dCfg<16>::LT : Ss2dCfg<4>::LT; }
 
-// consumer warps per CTA: the largest count <= maxw whose channel tile (32·cpt channels per warp) divides D;
+// warps per CTA: the largest count <= maxw whose channel tile (32·cpt channels per warp) divides D;
 // ragged D falls back to enough warps to cover it with a partially filled last CTA (TMA zero-fills, stores are
 // predicated)
 static int pick_warps(int D, int cpt, int maxw) {
