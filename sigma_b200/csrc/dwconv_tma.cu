@@ -1,10 +1,11 @@
 // Depthwise 3x3 (pad 1) + bias + SiLU on channels-last fp32 (vmamba.py:683-692,1072), TMA-tiled.
 //
-// A CTA owns a block of 32 channels (128 bytes of every pixel row) and walks spatial tiles of 8 x 32 output pixels
-// persistently.  Each tile's (8+2) x (32+2) x 32-channel input halo is ONE TMA box: out-of-bounds coordinates
+// A CTA owns a block of 32 channels (128 bytes of every pixel row) and walks spatial tiles of 8 x 16 output pixels
+// persistently.  Each tile's (8+2) x (16+2) x 32-channel input halo is ONE TMA box: out-of-bounds coordinates
 // (-1, H, W, channels >= D) are zero-filled by the TMA unit, which is exactly the convolution's zero padding, and
-// the x operand may be a strided view (the x half of in_proj's [x | z] rows).  Two ring slots: the next tile's box
-// is in flight while the current one is computed.  A thread produces 2 rows x 4 columns x 4 channels from a 4 x 6
+// the x operand may be a strided view (the x half of in_proj's [x | z] rows).  DC_NSLOT ring slots: the boxes of the
+// next DC_NSLOT-1 tiles are in flight while the current one is computed (a tile's compute is ~1/3 of its HBM time, so
+// with 2 slots the CTAs mostly waited for the one box in flight: 65 % of the HBM roofline).  A thread produces 2 rows x 4 columns x 4 channels from a 4 x 6
 // window read from shared memory (24 LDS.128 for 8 float4 outputs); the 9 taps of its channels live in registers.
 // HBM-bound: 8 bytes per output element (4 read + 4 written; halo re-reads hit L2).
 // The first version of this kernel read its window straight from global memory through L1 (18 loads per 4
@@ -15,7 +16,8 @@
 
 namespace sigma {
 
-constexpr int DC_CB = 32, DC_TW = 32, DC_TH = 8;
+constexpr int DC_CB = 32, DC_TW = 16, DC_TH = 8, DC_NSLOT = 4;
+constexpr int DC_THREADS = 8 * (DC_TW / 4) * (DC_TH / 2);          // 8 channel quads x column groups x row pairs
 constexpr int DC_TILE_FL = DC_CB * (DC_TW + 2) * (DC_TH + 2);
 constexpr int DC_TILE_BYTES = DC_TILE_FL * 4;
 
@@ -28,10 +30,10 @@ struct DwTmaParams {
   long long ntiles;
 };
 
-__global__ void __launch_bounds__(256, 2) dwconv3x3_silu_tma_kernel(const __grid_constant__ DwTmaParams p) {
+__global__ void __launch_bounds__(DC_THREADS, 2) dwconv3x3_silu_tma_kernel(const __grid_constant__ DwTmaParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float *tiles = reinterpret_cast<float *>(smem_raw);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * DC_TILE_BYTES);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + DC_NSLOT * DC_TILE_BYTES);
   __shared__ __align__(16) float sw[9][DC_CB];
   __shared__ __align__(16) float sb[DC_CB];
 
@@ -43,14 +45,13 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_silu_tma_kernel(const __grid
   }
   for (int i = tid; i < DC_CB; i += blockDim.x) sb[i] = (p.bias && c0 + i < p.D) ? p.bias[c0 + i] : 0.f;
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (int i = 0; i < DC_NSLOT; ++i) mbar_init(&full[i], 1);
     fence_mbar_init();
     tma_prefetch_desc(&p.map);
   }
   __syncthreads();
 
-  const int cq = tid & 7, wg = (tid >> 3) & 7, hp = tid >> 6;   // 8 channel quads x 8 column groups x 4 row pairs
+  const int cq = tid & 7, wg = (tid >> 3) % (DC_TW / 4), hp = (tid >> 3) / (DC_TW / 4);   // channel quad, column group, row pair
   float4 wt[9];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) wt[tap] = *reinterpret_cast<const float4 *>(&sw[tap][4 * cq]);
@@ -67,12 +68,15 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_silu_tma_kernel(const __grid
   };
 
   long long t = blockIdx.y;
-  if (tid == 0 && t < p.ntiles) issue(t, 0);
+  if (tid == 0)
+    for (int k = 0; k < DC_NSLOT - 1; ++k)
+      if (t + (long long)k * gridDim.y < p.ntiles) issue(t + (long long)k * gridDim.y, k);
+  int st = 0, ph = 0;
   for (int it = 0; t < p.ntiles; t += gridDim.y, ++it) {
-    const int st = it & 1;
-    const long long tn = t + gridDim.y;
-    if (tid == 0 && tn < p.ntiles) issue(tn, st ^ 1);   // slot st^1 was released by the barrier that ended iteration it-1
-    mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
+    const long long tn = t + (long long)(DC_NSLOT - 1) * gridDim.y;
+    // the slot of tile it-1 was released by the barrier that ended iteration it-1: refill it with tile it+NSLOT-1
+    if (tid == 0 && tn < p.ntiles) issue(tn, st == 0 ? DC_NSLOT - 1 : st - 1);
+    mbar_wait(&full[st], (uint32_t)ph);
 
     const int b = (int)(t / tiles_per_img);
     const int r = (int)(t - (long long)b * tiles_per_img);
@@ -124,6 +128,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_silu_tma_kernel(const __grid
       }
     }
     __syncthreads();   // every thread is done reading slot st before it is refilled
+    if (++st == DC_NSLOT) { st = 0; ph ^= 1; }
   }
 }
 
@@ -145,7 +150,7 @@ int dwconv3x3_silu_tma_launch(const float *x, long long x_row_stride, long long 
   p.ntiles = (long long)batch * p.tiles_w * p.tiles_h;
   if (p.ntiles == 0) return SIGMA_OK;
   const int cblocks = (D + DC_CB - 1) / DC_CB;
-  const size_t smem = 2 * DC_TILE_BYTES + 64;
+  const size_t smem = DC_NSLOT * DC_TILE_BYTES + 64;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(dwconv3x3_silu_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent over spatial tiles: 2 CTAs per SM in total, channel block fastest so that the CTAs working on one
   // spatial tile (adjacent 128-byte pieces of the same pixel rows) run at the same time
@@ -153,7 +158,7 @@ int dwconv3x3_silu_tma_launch(const float *x, long long x_row_stride, long long 
   // (never more CTAs than resident slots: a partial second wave of persistent CTAs would double the kernel time)
   const unsigned ny = (unsigned)std::max<long long>(1, std::min<long long>(p.ntiles, slots / cblocks));
   dim3 grid(cblocks, ny);
-  dwconv3x3_silu_tma_kernel<<<grid, 256, smem, stream>>>(p);
+  dwconv3x3_silu_tma_kernel<<<grid, DC_THREADS, smem, stream>>>(p);
   SIGMA_CHECK_LAUNCH();
   return SIGMA_OK;
 }
