@@ -117,3 +117,28 @@ def test_sigma_tiny_480x640_fused_vs_composed():
     agree = float((got.argmax(1) == ref.argmax(1)).float().mean())
     assert err <= 1e-2 * scale, f"logits differ by {err:.3e} (scale {scale:.3e})"
     assert agree >= 0.99, f"only {agree:.4f} of the arg-max labels agree"
+
+
+@pytest.mark.parametrize("backbone,Hh,Ww", [("sigma_small", 96, 128), ("sigma_base", 96, 160)])
+def test_other_backbones_fused_vs_composed(backbone, Hh, Ww):
+    """BASELINE.json configs 3-5 name Sigma-small and Sigma-base (dims 128..1024, dt_rank 8..64, 27-deep stage 3): the fused
+    path must agree with the composed path (op-level kernel pinned to the reference's goldens) for them as well."""
+    from sigma_b200 import modules as M
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(S)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.EncoderDecoder(cfg_tiny(Hh, Ww, num_classes=40, backbone=backbone), criterion=None).cuda().eval()
+    P.fill_state_dict(model, S)
+    rgb = torch.randn(1, 3, Hh, Ww, device="cuda")
+    mx = torch.randn(1, 3, Hh, Ww, device="cuda")
+    with torch.no_grad():
+        got = model(rgb, mx)
+        with M.composed_path():
+            ref = model(rgb, mx)
+    assert got.shape == ref.shape == (1, 40, Hh, Ww)
+    scale = float(ref.abs().max())
+    err = float((got - ref).abs().max())
+    agree = float((got.argmax(1) == ref.argmax(1)).float().mean())
+    assert err <= 2e-2 * scale, f"{backbone}: logits differ by {err:.3e} (scale {scale:.3e})"
+    assert agree >= 0.97, f"{backbone}: only {agree:.4f} of the arg-max labels agree"
