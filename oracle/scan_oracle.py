@@ -32,6 +32,17 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _threads(nthreads):
+    """0 = "the caller did not say": honour OMP_NUM_THREADS as it is NOW (the OpenMP runtime read it once when it was
+    loaded — possibly before bench.py or torchrun changed it), else leave the runtime's default."""
+    if nthreads:
+        return int(nthreads)
+    try:
+        return max(0, int(os.environ.get("OMP_NUM_THREADS", "0")))
+    except ValueError:
+        return 0
+
+
 def scan_fwd(u, delta, A, B, C, D=None, bias=None, softplus=False, nthreads=0):
     """numpy in / numpy out.  u, delta (b,d,L); A (d,N); B, C (b,G,N,L) or (b,N,L)."""
     u, delta, A, B, C, D, bias = map(_f, (u, delta, A, B, C, D, bias))
@@ -41,7 +52,7 @@ def scan_fwd(u, delta, A, B, C, D=None, bias=None, softplus=False, nthreads=0):
     G, N = B.shape[1], B.shape[2]
     out = np.empty_like(u)
     lib().sigma_oracle_scan_fwd(_p(u), _p(delta), _p(A), _p(B), _p(C), _p(D), _p(bias), _p(out),
-                                b, d, L, N, G, int(bool(softplus)), int(nthreads))
+                                b, d, L, N, G, int(bool(softplus)), _threads(nthreads))
     return out
 
 
@@ -55,5 +66,5 @@ def scan_bwd(u, delta, A, B, C, D, bias, dout, softplus=False, nthreads=0):
     dD, dbias = np.empty(d, np.float32), np.empty(d, np.float32)
     lib().sigma_oracle_scan_bwd(_p(u), _p(delta), _p(A), _p(B), _p(C), _p(D), _p(bias), _p(dout), _p(du),
                                 _p(ddelta), _p(dA), _p(dB), _p(dC), _p(dD), _p(dbias), b, d, L, N, G,
-                                int(bool(softplus)), int(nthreads))
+                                int(bool(softplus)), _threads(nthreads))
     return du, ddelta, dA, dB, dC, (dD if D is not None else None), (dbias if bias is not None else None)
