@@ -175,6 +175,18 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
     if (const char *e = getenv("SIGMA_SCAN_NST")) p.nst = std::max(2, std::min(Ss2dCfg<16>::MAX_NST, atoi(e)));
   }
   const int nthreads = 32 * NW;
+  // EXPERIMENTAL, off unless SIGMA_SCAN_POLY=1: polynomial exp2 for 2 of the 8 state pairs (ss2d_scan_poly_rp*.cu)
+  if (N == 16) {
+    static const bool poly = [] { const char *e = getenv("SIGMA_SCAN_POLY"); return e && atoi(e) > 0; }();
+    if (poly) {
+      switch (pad_rp(p.R)) {
+        case 8: return ss2d_launch<16, 1, 8, 2>(p, nthreads, stream);
+        case 12: return ss2d_launch<16, 1, 12, 2>(p, nthreads, stream);
+        case 24: return ss2d_launch<16, 1, 24, 2>(p, nthreads, stream);
+        case 48: return ss2d_launch<16, 1, 48, 2>(p, nthreads, stream);
+      }
+    }
+  }
   switch (N) {
     case 4: return dispatch_rp<4, 1>(p, nthreads, stream);
     case 8: return dispatch_rp<8, 1>(p, nthreads, stream);
