@@ -120,3 +120,29 @@ def test_full_model_golden(tag, H, W, Bn):
     agree = float((logits.argmax(1).numpy() == g["logits"].argmax(1)).mean())
     assert agree > 0.9995, agree
     assert abs(miou - float(g["miou"])) < 2e-4
+
+
+def test_oracle_port_matches_reference_at_the_benchmarked_size():
+    """Sigma-tiny 480x640 B=1 (BASELINE config 2): the oracle port against the fixture produced by the unmodified
+    reference at that size (tests/golden/make_golden_fullsize.py).  ~20-40 s on 8 cores."""
+    import contextlib
+    import io
+    from sigma_b200 import modules as M
+    tag, H, W, ncls = "sigma_tiny_480x640", 480, 640, 9
+    g = golden(tag)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.EncoderDecoder(cfg_tiny(H, W, num_classes=ncls), criterion=None)
+    P.fill_state_dict(model, SEED)
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    rgb = P.randn(SEED, tag + "/rgb", (1, 3, H, W))
+    mx = P.randn(SEED, tag + "/x", (1, 3, H, W))
+    with torch.no_grad():
+        logits = sigma_ref.encoder_decoder(rgb, mx, sd)
+    scale = float(g["logits_absmax"])
+    err = float(np.abs(logits[:, :, 3::8, 5::8].numpy() - g["logits_sub"]).max())
+    assert err <= 2e-4 * scale, f"oracle port vs reference at 480x640: {err:.3e} of {scale:.3e}"
+    pred = logits.argmax(1).numpy().astype(np.uint8)
+    assert float((pred == g["argmax"]).mean()) >= 0.9995
+    gt = (P.rand(SEED, tag + "/gt", (1, H, W)) * ncls).long().clamp(max=ncls - 1).numpy()
+    _, miou = sigma_ref.mean_iou(pred, gt, ncls)
+    assert abs(miou - float(g["miou"])) < 2e-4
