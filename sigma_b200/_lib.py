@@ -27,6 +27,7 @@ SIGNATURES = {
     "sigma_scan_fwd_f32_split": (c_int, [c_void_p] * 9 + [c_int] * 6 + [ctypes.POINTER(ScanStrides), c_void_p, c_size_t, c_int, c_void_p]),
     "sigma_scan_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "sigma_scan_bwd": (c_int, [c_void_p] * 15 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),
+    "sigma_scan_bwd_split": (c_int, [c_void_p] * 15 + [c_int] * 7 + [c_void_p, c_size_t, c_int, c_void_p]),
     "sigma_ss2d_padded_cp": (c_int, [c_int, c_int]),
     "sigma_ss2d_scan_workspace_bytes": (c_size_t, [c_int] * 6),
     "sigma_ss2d_scan_fwd": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),

@@ -1,6 +1,9 @@
 // C-ABI entry points (include/sigma_b200.h): argument checking, dtype staging, error strings.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include <atomic>
 
@@ -22,80 +25,69 @@ void set_error(const char *fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-// implemented in scan_op.cu
+// implemented in scan_op.cu (generic) / scan_op_tma.cu (TMA-staged) / scan_op_bwd*.cu
 size_t scan_op_workspace_bytes(int batch, int dim, int dstate);
-int scan_op_fwd_f32(const float *u, const float *delta, const float *A, const float *B, const float *C,
-                    const float *D, const float *bias, float *out, float *x, int batch, int dim, int L,
-                    int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
+size_t scan_op_tma_workspace_bytes(int batch, int dim, int dstate);
+size_t scan_op_bwd_workspace_bytes(int batch, int dim, int L, int N, int elem_bytes);
+size_t scan_op_bwd_tma_workspace_bytes(int batch, int dim, int L, int N, int elem_bytes);
+template <typename T>
+bool scan_op_tma_eligible(const void *u, const void *delta, const void *B, const void *C, const void *out, int dim, int L,
+                          int N, int G, const sigma_scan_strides &s);
+template <typename T>
+int scan_op_fwd_tma(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                    const float *bias, void *out, float *x, float *hs, int batch, int dim, int L, int N, int G, int softplus,
+                    const sigma_scan_strides &s, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream);
+template <typename T>
+int scan_op_fwd_generic(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                        const float *bias, void *out, float *x, float *hs, int batch, int dim, int L, int N, int G,
+                        int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes, int force_split,
+                        cudaStream_t stream);
+template <typename T>
+int scan_op_bwd_tma(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                    const float *bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC, float *dD,
+                    float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws, size_t ws_bytes,
                     int force_split, cudaStream_t stream);
+template <typename T>
+int scan_op_bwd_generic(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                        const float *bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                        float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
+                        size_t ws_bytes, cudaStream_t stream);
 
-// implemented in scan_op_bwd.cu
-size_t scan_op_bwd_workspace_bytes(int batch, int dim, int L, int N);
-int scan_op_bwd_f32(const float *u, const float *delta, const float *A, const float *B, const float *C, const float *D,
-                    const float *bias, const float *dout, float *du, float *ddelta, float *dA, float *dB, float *dC,
-                    float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
-                    size_t ws_bytes, cudaStream_t stream);
-
-// ---- half <-> float staging for the op-level boundary (u, delta, B, C, out may be fp16/bf16,
-// selective_scan.cpp:175-180; all arithmetic is fp32 either way) ----
-template <typename T>
-__device__ __forceinline__ float to_f32(T v);
-template <>
-__device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
-template <>
-__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-template <typename T>
-__device__ __forceinline__ T from_f32(float v);
-template <>
-__device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
-template <>
-__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
-
-// src (n0,n1,n2,L) with element strides (s0,s1,s2,1)  ->  dst contiguous fp32
-template <typename T>
-__global__ void cast_in_kernel(const T *__restrict__ src, float *__restrict__ dst, int n1, int n2, int L,
-                               long long s0, long long s1, long long s2, long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(i % L);
-    long long r = i / L;
-    const int i2 = (int)(r % n2); r /= n2;
-    const int i1 = (int)(r % n1); r /= n1;
-    dst[i] = to_f32<T>(src[r * s0 + i1 * s1 + i2 * s2 + l]);
-  }
-}
-// src contiguous fp32 (n0,n1,L) -> dst (n0,n1,L) with strides (s0,s1,1)
-template <typename T>
-__global__ void cast_out_kernel(const float *__restrict__ src, T *__restrict__ dst, int n1, int L,
-                                long long s0, long long s1, long long total) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int l = (int)(i % L);
-    long long r = i / L;
-    const int i1 = (int)(r % n1); r /= n1;
-    dst[r * s0 + i1 * s1 + l] = from_f32<T>(src[i]);
-  }
+// SIGMA_OP_GENERIC=1 forces the generic kernels (A/B timing, tests of the fallback on TMA-eligible shapes)
+static bool force_generic() {
+  const char *e = getenv("SIGMA_OP_GENERIC");
+  return e && atoi(e) > 0;
 }
 
 template <typename T>
-static int cast_in(const void *src, float *dst, int n0, int n1, int n2, int L, long long s0, long long s1,
-                   long long s2, cudaStream_t st) {
-  const long long total = (long long)n0 * n1 * n2 * L;
-  if (total == 0) return SIGMA_OK;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  cast_in_kernel<T><<<blocks, 256, 0, st>>>((const T *)src, dst, n1, n2, L, s0, s1, s2, total);
-  SIGMA_CHECK_LAUNCH();
-  return SIGMA_OK;
+static int scan_fwd_dispatch(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                             const float *bias, void *out, float *x, int batch, int dim, int L, int N, int G, int softplus,
+                             const sigma_scan_strides &s, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream) {
+  if (!force_generic() && scan_op_tma_eligible<T>(u, delta, B, C, out, dim, L, N, G, s))
+    return scan_op_fwd_tma<T>(u, delta, A, B, C, D, bias, out, x, nullptr, batch, dim, L, N, G, softplus, s, ws, ws_bytes,
+                              force_split, stream);
+  return scan_op_fwd_generic<T>(u, delta, A, B, C, D, bias, out, x, nullptr, batch, dim, L, N, G, softplus, s, ws, ws_bytes,
+                                force_split, stream);
 }
+
 template <typename T>
-static int cast_out(const float *src, void *dst, int n0, int n1, int L, long long s0, long long s1,
-                    cudaStream_t st) {
-  const long long total = (long long)n0 * n1 * L;
-  if (total == 0) return SIGMA_OK;
-  const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  cast_out_kernel<T><<<blocks, 256, 0, st>>>(src, (T *)dst, n1, L, s0, s1, total);
-  SIGMA_CHECK_LAUNCH();
-  return SIGMA_OK;
+static int scan_bwd_dispatch(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                             const float *bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                             float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
+                             size_t ws_bytes, int force_split, cudaStream_t stream) {
+  sigma_scan_strides st;   // contiguous
+  st.u_batch = st.delta_batch = st.out_batch = (int64_t)dim * L;
+  st.u_dim = st.delta_dim = st.out_dim = L;
+  st.A_dim = N; st.A_dstate = 1;
+  st.B_batch = st.C_batch = (int64_t)G * N * L;
+  st.B_group = st.C_group = (int64_t)N * L;
+  st.B_dstate = st.C_dstate = L;
+  const bool al = (((uintptr_t)dout | (uintptr_t)du | (uintptr_t)ddelta | (uintptr_t)dB | (uintptr_t)dC) & 15) == 0;
+  if (!force_generic() && al && scan_op_tma_eligible<T>(u, delta, B, C, du, dim, L, N, G, st))
+    return scan_op_bwd_tma<T>(u, delta, A, B, C, D, bias, dout, du, ddelta, dA, dB, dC, dD, dbias, batch, dim, L, N, G, softplus,
+                              ws, ws_bytes, force_split, stream);
+  return scan_op_bwd_generic<T>(u, delta, A, B, C, D, bias, dout, du, ddelta, dA, dB, dC, dD, dbias, batch, dim, L, N, G,
+                                softplus, ws, ws_bytes, stream);
 }
 
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -112,13 +104,8 @@ const char *sigma_last_error(void) { return g_err; }
 uint64_t sigma_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t sigma_scan_fwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype) {
-  size_t w = align256(scan_op_workspace_bytes(batch, dim, dstate));
-  if (dtype != SIGMA_F32) {
-    const size_t bdl = (size_t)batch * dim * seqlen * sizeof(float);
-    const size_t bgnl = (size_t)batch * ngroups * dstate * seqlen * sizeof(float);
-    w += 3 * align256(bdl) + 2 * align256(bgnl);
-  }
-  return w;
+  (void)seqlen; (void)ngroups; (void)dtype;   // every element type is read natively: only the L-segment carries need scratch
+  return align256(std::max(scan_op_workspace_bytes(batch, dim, dstate), scan_op_tma_workspace_bytes(batch, dim, dstate)));
 }
 
 int sigma_scan_fwd(const void *u, const void *delta, const float *A, const void *B, const void *C,
@@ -134,50 +121,14 @@ int sigma_scan_fwd(const void *u, const void *delta, const float *A, const void 
   SIGMA_CHECK_ARG(dim % ngroups == 0, "sigma_scan_fwd: dim=%d not divisible by ngroups=%d", dim, ngroups);
   SIGMA_CHECK_ARG(dtype == SIGMA_F32 || dtype == SIGMA_F16 || dtype == SIGMA_BF16,
                   "sigma_scan_fwd: unknown dtype %d", dtype);
-
-  if (dtype == SIGMA_F32) {
-    return scan_op_fwd_f32((const float *)u, (const float *)delta, A, (const float *)B, (const float *)C, D,
-                           delta_bias, (float *)out, x, batch, dim, seqlen, dstate, ngroups, delta_softplus,
-                           *st, workspace, workspace_bytes, 0, stream);
-  }
-  // fp16 / bf16: stage through fp32 scratch
-  const size_t need = sigma_scan_fwd_workspace_bytes(batch, dim, seqlen, dstate, ngroups, dtype);
-  if (workspace == nullptr || workspace_bytes < need) {
-    set_error("sigma_scan_fwd: half-precision I/O needs %zu workspace bytes, got %zu", need, workspace_bytes);
-    return SIGMA_EWORKSPACE;
-  }
-  char *w = (char *)workspace;
-  const size_t carry_b = align256(scan_op_workspace_bytes(batch, dim, dstate));
-  const size_t bdl = align256((size_t)batch * dim * seqlen * sizeof(float));
-  const size_t bgnl = align256((size_t)batch * ngroups * dstate * seqlen * sizeof(float));
-  float *u32 = (float *)(w + carry_b), *d32 = (float *)(w + carry_b + bdl), *o32 = (float *)(w + carry_b + 2 * bdl);
-  float *B32 = (float *)(w + carry_b + 3 * bdl), *C32 = (float *)(w + carry_b + 3 * bdl + bgnl);
-  int rc;
-#define CAST_ALL(T)                                                                                          \
-  do {                                                                                                       \
-    if ((rc = cast_in<T>(u, u32, batch, dim, 1, seqlen, st->u_batch, st->u_dim, 0, stream))) return rc;      \
-    if ((rc = cast_in<T>(delta, d32, batch, dim, 1, seqlen, st->delta_batch, st->delta_dim, 0, stream)))     \
-      return rc;                                                                                             \
-    if ((rc = cast_in<T>(B, B32, batch, ngroups, dstate, seqlen, st->B_batch, st->B_group, st->B_dstate,     \
-                         stream)))                                                                           \
-      return rc;                                                                                             \
-    if ((rc = cast_in<T>(C, C32, batch, ngroups, dstate, seqlen, st->C_batch, st->C_group, st->C_dstate,     \
-                         stream)))                                                                           \
-      return rc;                                                                                             \
-  } while (0)
-  if (dtype == SIGMA_F16) CAST_ALL(__half); else CAST_ALL(__nv_bfloat16);
-#undef CAST_ALL
-  sigma_scan_strides cs = *st;
-  cs.u_batch = cs.delta_batch = cs.out_batch = (int64_t)dim * seqlen;
-  cs.u_dim = cs.delta_dim = cs.out_dim = seqlen;
-  cs.B_batch = cs.C_batch = (int64_t)ngroups * dstate * seqlen;
-  cs.B_group = cs.C_group = (int64_t)dstate * seqlen;
-  cs.B_dstate = cs.C_dstate = seqlen;
-  rc = scan_op_fwd_f32(u32, d32, A, B32, C32, D, delta_bias, o32, x, batch, dim, seqlen, dstate, ngroups,
-                       delta_softplus, cs, workspace, carry_b, 0, stream);
-  if (rc) return rc;
-  if (dtype == SIGMA_F16) return cast_out<__half>(o32, out, batch, dim, seqlen, st->out_batch, st->out_dim, stream);
-  return cast_out<__nv_bfloat16>(o32, out, batch, dim, seqlen, st->out_batch, st->out_dim, stream);
+  if (dtype == SIGMA_F32)
+    return scan_fwd_dispatch<float>(u, delta, A, B, C, D, delta_bias, out, x, batch, dim, seqlen, dstate, ngroups, delta_softplus,
+                                    *st, workspace, workspace_bytes, 0, stream);
+  if (dtype == SIGMA_F16)
+    return scan_fwd_dispatch<__half>(u, delta, A, B, C, D, delta_bias, out, x, batch, dim, seqlen, dstate, ngroups, delta_softplus,
+                                     *st, workspace, workspace_bytes, 0, stream);
+  return scan_fwd_dispatch<__nv_bfloat16>(u, delta, A, B, C, D, delta_bias, out, x, batch, dim, seqlen, dstate, ngroups,
+                                          delta_softplus, *st, workspace, workspace_bytes, 0, stream);
 }
 
 // test hook (not part of the drop-in surface): force the number of L-segments of the fp32 op kernel
@@ -188,8 +139,8 @@ int sigma_scan_fwd_f32_split(const float *u, const float *delta, const float *A,
                              int nsplit, void *stream) {
   SIGMA_CHECK_ARG(u && delta && A && B && C && out && st, "sigma_scan_fwd_f32_split: null pointer argument");
   SIGMA_CHECK_ARG(dim % ngroups == 0 && dstate <= 256, "sigma_scan_fwd_f32_split: bad dim/ngroups/dstate");
-  return scan_op_fwd_f32(u, delta, A, B, C, D, delta_bias, out, x, batch, dim, seqlen, dstate, ngroups,
-                         delta_softplus, *st, workspace, workspace_bytes, nsplit, (cudaStream_t)stream);
+  return scan_fwd_dispatch<float>(u, delta, A, B, C, D, delta_bias, out, x, batch, dim, seqlen, dstate, ngroups,
+                                  delta_softplus, *st, workspace, workspace_bytes, nsplit, (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop
@@ -368,62 +319,54 @@ int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const f
 }
 
 size_t sigma_scan_bwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype) {
-  size_t w = align256(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate));
-  if (dtype != SIGMA_F32) {
-    const size_t bdl = align256((size_t)batch * dim * seqlen * sizeof(float));
-    const size_t bgnl = align256((size_t)batch * ngroups * dstate * seqlen * sizeof(float));
-    w += 5 * bdl + 2 * bgnl;   // u, delta, dout, du, ddelta + B, C
-  }
-  return w;
+  (void)ngroups;
+  const int eb = dtype == SIGMA_F32 ? 4 : 2;
+  return align256(std::max(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate, eb),
+                           scan_op_bwd_tma_workspace_bytes(batch, dim, seqlen, std::min(dstate, 16), eb)));
 }
 
-int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
-                   const float *delta_bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
-                   float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
-                   int delta_softplus, void *workspace, size_t workspace_bytes, void *stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+static int scan_bwd_entry(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                          const float *delta_bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                          float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
+                          int delta_softplus, void *workspace, size_t workspace_bytes, int force_split, cudaStream_t stream) {
   SIGMA_CHECK_ARG(u && delta && A && B && C && dout && du && ddelta && dA && dB && dC, "sigma_scan_bwd: null pointer argument");
   SIGMA_CHECK_ARG((D == nullptr || dD != nullptr) && (delta_bias == nullptr || ddelta_bias != nullptr),
                   "sigma_scan_bwd: dD / ddelta_bias required when D / delta_bias are given");
   SIGMA_CHECK_ARG(batch > 0 && dim > 0 && seqlen > 0 && dstate > 0 && ngroups > 0 && dim % ngroups == 0,
                   "sigma_scan_bwd: bad sizes (batch=%d dim=%d seqlen=%d dstate=%d ngroups=%d)", batch, dim, seqlen, dstate, ngroups);
   SIGMA_CHECK_ARG(dtype == SIGMA_F32 || dtype == SIGMA_F16 || dtype == SIGMA_BF16, "sigma_scan_bwd: unknown dtype %d", dtype);
+  if (dstate > 16) { set_error("sigma_scan_bwd: d_state=%d > 16 is not supported by the backward kernels", dstate); return SIGMA_EUNSUPPORTED; }
   const size_t need = sigma_scan_bwd_workspace_bytes(batch, dim, seqlen, dstate, ngroups, dtype);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("sigma_scan_bwd: needs %zu workspace bytes, got %zu", need, workspace_bytes);
     return SIGMA_EWORKSPACE;
   }
-  const size_t core_b = align256(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate));
   if (dtype == SIGMA_F32)
-    return scan_op_bwd_f32((const float *)u, (const float *)delta, A, (const float *)B, (const float *)C, D, delta_bias,
-                           (const float *)dout, (float *)du, (float *)ddelta, dA, dB, dC, dD, ddelta_bias, batch, dim, seqlen,
-                           dstate, ngroups, delta_softplus, workspace, core_b, stream);
-  char *w = (char *)workspace + core_b;
-  const size_t bdl = align256((size_t)batch * dim * seqlen * sizeof(float));
-  const size_t bgnl = align256((size_t)batch * ngroups * dstate * seqlen * sizeof(float));
-  float *u32 = (float *)w, *d32 = (float *)(w + bdl), *o32 = (float *)(w + 2 * bdl), *du32 = (float *)(w + 3 * bdl),
-        *dd32 = (float *)(w + 4 * bdl), *B32 = (float *)(w + 5 * bdl), *C32 = (float *)(w + 5 * bdl + bgnl);
-  const long long sb = (long long)dim * seqlen, sg = (long long)dstate * seqlen, sbb = (long long)ngroups * sg;
-  int rc;
-#define CAST_ALL(T)                                                                                   \
-  do {                                                                                                \
-    if ((rc = cast_in<T>(u, u32, batch, dim, 1, seqlen, sb, seqlen, 0, stream))) return rc;            \
-    if ((rc = cast_in<T>(delta, d32, batch, dim, 1, seqlen, sb, seqlen, 0, stream))) return rc;        \
-    if ((rc = cast_in<T>(dout, o32, batch, dim, 1, seqlen, sb, seqlen, 0, stream))) return rc;         \
-    if ((rc = cast_in<T>(B, B32, batch, ngroups, dstate, seqlen, sbb, sg, seqlen, stream))) return rc; \
-    if ((rc = cast_in<T>(C, C32, batch, ngroups, dstate, seqlen, sbb, sg, seqlen, stream))) return rc; \
-  } while (0)
-  if (dtype == SIGMA_F16) CAST_ALL(__half); else CAST_ALL(__nv_bfloat16);
-#undef CAST_ALL
-  rc = scan_op_bwd_f32(u32, d32, A, B32, C32, D, delta_bias, o32, du32, dd32, dA, dB, dC, dD, ddelta_bias, batch, dim, seqlen,
-                       dstate, ngroups, delta_softplus, workspace, core_b, stream);
-  if (rc) return rc;
-  if (dtype == SIGMA_F16) {
-    if ((rc = cast_out<__half>(du32, du, batch, dim, seqlen, sb, seqlen, stream))) return rc;
-    return cast_out<__half>(dd32, ddelta, batch, dim, seqlen, sb, seqlen, stream);
-  }
-  if ((rc = cast_out<__nv_bfloat16>(du32, du, batch, dim, seqlen, sb, seqlen, stream))) return rc;
-  return cast_out<__nv_bfloat16>(dd32, ddelta, batch, dim, seqlen, sb, seqlen, stream);
+    return scan_bwd_dispatch<float>(u, delta, A, B, C, D, delta_bias, dout, du, ddelta, dA, dB, dC, dD, ddelta_bias, batch, dim,
+                                    seqlen, dstate, ngroups, delta_softplus, workspace, workspace_bytes, force_split, stream);
+  if (dtype == SIGMA_F16)
+    return scan_bwd_dispatch<__half>(u, delta, A, B, C, D, delta_bias, dout, du, ddelta, dA, dB, dC, dD, ddelta_bias, batch, dim,
+                                     seqlen, dstate, ngroups, delta_softplus, workspace, workspace_bytes, force_split, stream);
+  return scan_bwd_dispatch<__nv_bfloat16>(u, delta, A, B, C, D, delta_bias, dout, du, ddelta, dA, dB, dC, dD, ddelta_bias, batch,
+                                          dim, seqlen, dstate, ngroups, delta_softplus, workspace, workspace_bytes, force_split,
+                                          stream);
+}
+
+int sigma_scan_bwd(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                   const float *delta_bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                   float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
+                   int delta_softplus, void *workspace, size_t workspace_bytes, void *stream_) {
+  return scan_bwd_entry(u, delta, A, B, C, D, delta_bias, dout, du, ddelta, dA, dB, dC, dD, ddelta_bias, batch, dim, seqlen,
+                        dstate, ngroups, dtype, delta_softplus, workspace, workspace_bytes, 0, (cudaStream_t)stream_);
+}
+
+// test hook: force the number of L-segments of the backward
+int sigma_scan_bwd_split(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                         const float *delta_bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                         float *dD, float *ddelta_bias, int batch, int dim, int seqlen, int dstate, int ngroups, int dtype,
+                         int delta_softplus, void *workspace, size_t workspace_bytes, int nsplit, void *stream_) {
+  return scan_bwd_entry(u, delta, A, B, C, D, delta_bias, dout, du, ddelta, dA, dB, dC, dD, ddelta_bias, batch, dim, seqlen,
+                        dstate, ngroups, dtype, delta_softplus, workspace, workspace_bytes, nsplit, (cudaStream_t)stream_);
 }
 
 int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *bias, const float *residual, int64_t ldr,

@@ -1,5 +1,7 @@
-// a1 — op-level selective scan forward, drop-in for selective_scan_cuda_core.fwd
+// a1 — op-level selective scan forward, GENERIC path: any strides / ragged rows / any d_state <= 256 / channel groups
+// that are not a multiple of 32.  Shapes TMA can express (every Sigma call) take scan_op_tma.cu instead.
 // (reference: csrc/selective_scan/selective_scan.cpp:165-249, selective_scan_fwd_kernel.cuh:64-206).
+// fp16 / bf16 are read and written natively (converted on the way into / out of shared memory; all arithmetic fp32).
 //
 // Layout is the reference's: u/delta/out (B, KD, L) and B/C (B, G, N, L), L contiguous.  A CTA owns
 // 32 channels of one (batch, group) and walks L in tiles of 32 positions; tiles are staged in
@@ -11,6 +13,9 @@
 // them, MODE_APPLY redoes the segment from its true start state and writes out.
 #include <algorithm>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "scan_core.cuh"
 
 namespace sigma {
@@ -20,9 +25,20 @@ constexpr int OP_LTP = 36;  // smem row pitch (floats)
 constexpr int OP_DT = 32;   // channels per CTA
 constexpr int OP_NST = 2;   // cp.async stages
 
+template <typename T> __device__ __forceinline__ float gen_to_f32(T v);
+template <> __device__ __forceinline__ float gen_to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float gen_to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float gen_to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T gen_from_f32(float v);
+template <> __device__ __forceinline__ float gen_from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half gen_from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 gen_from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
 struct ScanOpParams {
-  const float *u, *delta, *A, *B, *C, *D, *bias;
-  float *out, *x, *carry;
+  const void *u, *delta, *B, *C;   // element type T of the kernel instantiation
+  const float *A, *D, *bias;
+  void *out;
+  float *x, *carry;
   float *hs;  // optional: state at the START of every 32-position tile, (batch, dim, ntiles, NP) — consumed by the backward
   int batch, dim, L, N, G, dpg, tiles_per_group;
   int softplus;
@@ -35,8 +51,9 @@ __host__ __device__ constexpr int op_smem_floats(int NP) {
   return OP_NST * (2 * OP_DT + 2 * NP) * OP_LTP + OP_DT * OP_LTP;
 }
 
-template <int SPT, int LPC, int MODE>
+template <typename T, int SPT, int LPC, int MODE>
 __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p) {
+  constexpr bool F32 = sizeof(T) == 4;
   constexpr int NP = SPT * LPC;        // padded state count
   constexpr int CPW = 32 / LPC;        // channels per warp
   constexpr int NTHREADS = 32 * LPC;   // OP_DT / CPW warps
@@ -61,10 +78,10 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
   const int t0 = split * p.tiles_per_split;
   const int t1 = min(p.ntiles, t0 + p.tiles_per_split);
 
-  const float *gu = p.u + (long long)b * p.u_b + (long long)d0 * p.u_d;
-  const float *gdl = p.delta + (long long)b * p.dl_b + (long long)d0 * p.dl_d;
-  const float *gB = p.B + (long long)b * p.B_b + (long long)g * p.B_g;
-  const float *gC = p.C + (long long)b * p.C_b + (long long)g * p.C_g;
+  const T *gu = (const T *)p.u + (long long)b * p.u_b + (long long)d0 * p.u_d;
+  const T *gdl = (const T *)p.delta + (long long)b * p.dl_b + (long long)d0 * p.dl_d;
+  const T *gB = (const T *)p.B + (long long)b * p.B_b + (long long)g * p.B_g;
+  const T *gC = (const T *)p.C + (long long)b * p.C_b + (long long)g * p.C_g;
 
   // --- per-thread constants ---
   float a2[SPT], h[SPT];
@@ -84,18 +101,18 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
   }
   const float bias = (p.bias && ch_ok) ? p.bias[d] : 0.f;
   const float Dv = (p.D && ch_ok) ? p.D[d] : 0.f;
-  float sumdl = 0.f;  // Σ delta' since the last checkpoint (per channel, identical on its LPC lanes)
+  float sumdl = 0.f;  // Σ delta' since the start of this CTA's walk (per channel, identical on its LPC lanes)
 
   // --- tile loader: rows [0,32) u, [32,64) delta, [64,64+NP) B, [64+NP,64+2NP) C ---
   auto load_tile = [&](int t, int st) {
     float *sbase = smem + st * STAGE_ROWS * OP_LTP;
     const int l0 = t * OP_LT;
     constexpr int ROWS = WITH_Y ? STAGE_ROWS : (2 * OP_DT + NP);
-    if (p.vec_in) {
+    if (F32 && p.vec_in) {
       for (int i = tid; i < ROWS * (OP_LT / 4); i += NTHREADS) {
         const int row = i >> 3, ck = i & 7;
         const int l = l0 + ck * 4;
-        const float *src;
+        const T *src;
         bool ok;
         if (row < OP_DT) { ok = row < nch; src = gu + (long long)row * p.u_d; }
         else if (row < 2 * OP_DT) { ok = (row - OP_DT) < nch; src = gdl + (long long)(row - OP_DT) * p.dl_d; }
@@ -103,20 +120,21 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
         else { const int n = row - 2 * OP_DT - NP; ok = n < p.N; src = gC + (long long)n * p.C_n; }
         int nb = ok ? min(4, p.L - l) * 4 : 0;
         nb = max(nb, 0);
-        cp_async16(sbase + row * OP_LTP + ck * 4, nb > 0 ? (const void *)(src + l) : (const void *)p.u, nb);
+        if constexpr (F32) cp_async16(sbase + row * OP_LTP + ck * 4, nb > 0 ? (const void *)(src + l) : (const void *)p.u, nb);
       }
     } else {
       for (int i = tid; i < ROWS * OP_LT; i += NTHREADS) {
         const int row = i >> 5, e = i & 31;
         const int l = l0 + e;
-        const float *src;
+        const T *src;
         bool ok;
         if (row < OP_DT) { ok = row < nch; src = gu + (long long)row * p.u_d; }
         else if (row < 2 * OP_DT) { ok = (row - OP_DT) < nch; src = gdl + (long long)(row - OP_DT) * p.dl_d; }
         else if (row < 2 * OP_DT + NP) { const int n = row - 2 * OP_DT; ok = n < p.N; src = gB + (long long)n * p.B_n; }
         else { const int n = row - 2 * OP_DT - NP; ok = n < p.N; src = gC + (long long)n * p.C_n; }
         ok = ok && l < p.L;
-        cp_async4(sbase + row * OP_LTP + e, ok ? (const void *)(src + l) : (const void *)p.u, ok ? 4 : 0);
+        if constexpr (F32) cp_async4(sbase + row * OP_LTP + e, ok ? (const void *)(src + l) : (const void *)p.u, ok ? 4 : 0);
+        else sbase[row * OP_LTP + e] = ok ? gen_to_f32<T>(src[l]) : 0.f;   // 16-bit elements: plain load, widened on the way in
       }
     }
   };
@@ -195,13 +213,13 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
     if (WITH_Y) {
       __syncwarp();
       // this warp's CPW rows of the y tile -> global, 128-byte rows
-      float *go = p.out + (long long)b * p.o_b + (long long)d0 * p.o_d + (long long)t * OP_LT;
-      if (p.vec_out) {
+      T *go = (T *)p.out + (long long)b * p.o_b + (long long)d0 * p.o_d + (long long)t * OP_LT;
+      if (F32 && p.vec_out) {
         for (int i = lane; i < CPW * (OP_LT / 4); i += 32) {
           const int r = warp * CPW + (i >> 3), ck = i & 7;
           if (r < nch && 4 * ck < npos) {
             const float4 v = *reinterpret_cast<const float4 *>(sY + r * OP_LTP + 4 * ck);
-            float *dst = go + (long long)r * p.o_d + 4 * ck;
+            float *dst = (float *)go + (long long)r * p.o_d + 4 * ck;
             if (4 * ck + 4 <= npos) *reinterpret_cast<float4 *>(dst) = v;
             else {
               dst[0] = v.x;
@@ -213,7 +231,7 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
       } else {
         for (int rr = 0; rr < CPW; ++rr) {
           const int r = warp * CPW + rr;
-          if (r < nch && lane < npos) go[(long long)r * p.o_d + lane] = sY[r * OP_LTP + lane];
+          if (r < nch && lane < npos) go[(long long)r * p.o_d + lane] = gen_from_f32<T>(sY[r * OP_LTP + lane]);
         }
       }
       // x checkpoints: (prod a, h) at the end of every 2048-chunk (selective_scan_fwd_kernel.cuh:181-184)
@@ -226,13 +244,14 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
 #pragma unroll
             for (int s = 0; s < SPT; ++s) {
               const int n = q * SPT + s;
-              if (n < p.N) {
-                xr[2 * n] = ex2(a2[s] * sumdl);
+              if (n < p.N) {   // (prod a since the SEQUENCE start, h): SSMScanPrefixCallbackOp's running prefix
+                float P = ex2(a2[s] * sumdl);
+                if (MODE == MODE_APPLY) P *= carry_row[q * SPT + s];
+                xr[2 * n] = P;
                 xr[2 * n + 1] = h[s];
               }
             }
           }
-          sumdl = 0.f;
         }
       }
     }
@@ -249,18 +268,21 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_kernel(const ScanOpParams p)
   }
 }
 
-// carry[row][split] = (P, h_local_end) -> (P, H_start): H_0 = 0, H_{s+1} = P_s·H_s + h_s
+// carry[row][split] = (P, h_local_end) -> (product of P over the PRECEDING segments, H_start):
+// H_0 = 0, H_{s+1} = P_s·H_s + h_s.  (The prefix product feeds the running-prefix component of the chunk states `x`.)
 __global__ void scan_combine_kernel(float *carry, long long nrows, int nsplit, int NP) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nrows * NP) return;
   const long long row = idx / NP;
   const int n = (int)(idx - row * NP);
-  float H = 0.f;
+  float H = 0.f, Pc = 1.f;
   for (int s = 0; s < nsplit; ++s) {
     float *base = carry + (row * nsplit + s) * 2 * NP;
     const float P = base[n], hl = base[NP + n];
+    base[n] = Pc;
     base[NP + n] = H;
     H = fmaf(P, H, hl);
+    Pc *= P;
   }
 }
 
@@ -275,7 +297,7 @@ static int pick_npad(int N) {
   return 256;
 }
 
-template <int SPT, int LPC>
+template <typename T, int SPT, int LPC>
 static int launch_scan_op(ScanOpParams &p, cudaStream_t stream) {
   constexpr int NP = SPT * LPC;
   const size_t smem = (size_t)op_smem_floats(NP) * sizeof(float);
@@ -285,19 +307,19 @@ static int launch_scan_op(ScanOpParams &p, cudaStream_t stream) {
     return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   };
   if (p.nsplit == 1) {
-    SIGMA_CHECK_CUDA(set_attr((const void *)scan_op_kernel<SPT, LPC, MODE_SERIAL>));
-    scan_op_kernel<SPT, LPC, MODE_SERIAL><<<grid, block, smem, stream>>>(p);
+    SIGMA_CHECK_CUDA(set_attr((const void *)scan_op_kernel<T, SPT, LPC, MODE_SERIAL>));
+    scan_op_kernel<T, SPT, LPC, MODE_SERIAL><<<grid, block, smem, stream>>>(p);
     SIGMA_CHECK_LAUNCH();
   } else {
-    SIGMA_CHECK_CUDA(set_attr((const void *)scan_op_kernel<SPT, LPC, MODE_SUMMARY>));
-    SIGMA_CHECK_CUDA(set_attr((const void *)scan_op_kernel<SPT, LPC, MODE_APPLY>));
-    scan_op_kernel<SPT, LPC, MODE_SUMMARY><<<grid, block, smem, stream>>>(p);
+    SIGMA_CHECK_CUDA(set_attr((const void *)scan_op_kernel<T, SPT, LPC, MODE_SUMMARY>));
+    SIGMA_CHECK_CUDA(set_attr((const void *)scan_op_kernel<T, SPT, LPC, MODE_APPLY>));
+    scan_op_kernel<T, SPT, LPC, MODE_SUMMARY><<<grid, block, smem, stream>>>(p);
     SIGMA_CHECK_LAUNCH();
     const long long nrows = (long long)p.batch * p.dim;
     const long long tot = nrows * NP;
     scan_combine_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, stream>>>(p.carry, nrows, p.nsplit, NP);
     SIGMA_CHECK_LAUNCH();
-    scan_op_kernel<SPT, LPC, MODE_APPLY><<<grid, block, smem, stream>>>(p);
+    scan_op_kernel<T, SPT, LPC, MODE_APPLY><<<grid, block, smem, stream>>>(p);
     SIGMA_CHECK_LAUNCH();
   }
   return SIGMA_OK;
@@ -325,25 +347,15 @@ size_t scan_op_workspace_bytes(int batch, int dim, int dstate) {
   return (size_t)batch * dim * 64 * 2 * pick_npad(dstate) * sizeof(float);
 }
 
-int scan_op_fwd_f32_hs(const float *u, const float *delta, const float *A, const float *B, const float *C,
-                       const float *D, const float *bias, float *out, float *x, float *hs, int batch, int dim, int L,
-                       int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
-                       int force_split, cudaStream_t stream);
-
-int scan_op_fwd_f32(const float *u, const float *delta, const float *A, const float *B, const float *C,
-                    const float *D, const float *bias, float *out, float *x, int batch, int dim, int L,
-                    int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
-                    int force_split, cudaStream_t stream) {
-  return scan_op_fwd_f32_hs(u, delta, A, B, C, D, bias, out, x, nullptr, batch, dim, L, N, G, softplus, s, ws, ws_bytes,
-                            force_split, stream);
-}
-
 int scan_op_npad(int N) { return pick_npad(N); }
 
-int scan_op_fwd_f32_hs(const float *u, const float *delta, const float *A, const float *B, const float *C,
-                       const float *D, const float *bias, float *out, float *x, float *hs, int batch, int dim, int L,
-                       int N, int G, int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes,
-                       int force_split, cudaStream_t stream) {
+// `hs` (nullable): state at the start of every 32-position tile, (batch, dim, ntiles, NP) — forces a single pass.
+// d_state > 16 runs with up to 16 lanes per channel (8-16 states per lane) so that no instantiation spills.
+template <typename T>
+int scan_op_fwd_generic(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                        const float *bias, void *out, float *x, float *hs, int batch, int dim, int L, int N, int G,
+                        int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes, int force_split,
+                        cudaStream_t stream) {
   ScanOpParams p;
   p.hs = hs;
   if (hs != nullptr) force_split = 1;  // checkpoints are written by the serial walk only
@@ -360,24 +372,33 @@ int scan_op_fwd_f32_hs(const float *u, const float *delta, const float *A, const
   p.nchunks = (L + 2047) / 2048;
   auto al16 = [](const void *ptr) { return ((uintptr_t)ptr & 15) == 0; };
   auto m4 = [](long long v) { return (v & 3) == 0; };
-  p.vec_in = al16(u) && al16(delta) && al16(B) && al16(C) && m4(p.u_b) && m4(p.u_d) && m4(p.dl_b) &&
+  p.vec_in = sizeof(T) == 4 && al16(u) && al16(delta) && al16(B) && al16(C) && m4(p.u_b) && m4(p.u_d) && m4(p.dl_b) &&
              m4(p.dl_d) && m4(p.B_b) && m4(p.B_g) && m4(p.B_n) && m4(p.C_b) && m4(p.C_g) && m4(p.C_n);
-  p.vec_out = al16(out) && m4(p.o_b) && m4(p.o_d);
+  p.vec_out = sizeof(T) == 4 && al16(out) && m4(p.o_b) && m4(p.o_d);
 
   const int NP = pick_npad(N);
-  const int lpc = NP <= 4 ? 1 : (NP <= 8 ? 2 : 4);
+  const int lpc = NP <= 4 ? 1 : (NP <= 8 ? 2 : (NP <= 32 ? 4 : (NP <= 128 ? NP / 8 : 16)));
   const bool have_ws = ws != nullptr && ws_bytes >= scan_op_workspace_bytes(batch, dim, N);
   plan_split(p, lpc, have_ws, force_split);
 
   switch (NP) {
-    case 4: return launch_scan_op<4, 1>(p, stream);
-    case 8: return launch_scan_op<4, 2>(p, stream);
-    case 16: return launch_scan_op<4, 4>(p, stream);
-    case 32: return launch_scan_op<8, 4>(p, stream);
-    case 64: return launch_scan_op<16, 4>(p, stream);
-    case 128: return launch_scan_op<32, 4>(p, stream);
-    default: return launch_scan_op<64, 4>(p, stream);
+    case 4: return launch_scan_op<T, 4, 1>(p, stream);
+    case 8: return launch_scan_op<T, 4, 2>(p, stream);
+    case 16: return launch_scan_op<T, 4, 4>(p, stream);
+    case 32: return launch_scan_op<T, 8, 4>(p, stream);
+    case 64: return launch_scan_op<T, 8, 8>(p, stream);
+    case 128: return launch_scan_op<T, 8, 16>(p, stream);
+    default: return launch_scan_op<T, 16, 16>(p, stream);
   }
 }
+
+#define SIGMA_INST(T)                                                                                                       \
+  template int scan_op_fwd_generic<T>(const void *, const void *, const float *, const void *, const void *, const float *, \
+                                      const float *, void *, float *, float *, int, int, int, int, int, int,               \
+                                      const sigma_scan_strides &, void *, size_t, int, cudaStream_t);
+SIGMA_INST(float)
+SIGMA_INST(__half)
+SIGMA_INST(__nv_bfloat16)
+#undef SIGMA_INST
 
 }  // namespace sigma

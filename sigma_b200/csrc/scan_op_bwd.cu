@@ -1,5 +1,7 @@
-// a3 — op-level selective scan backward, drop-in for selective_scan_cuda_core.bwd
+// a3 — op-level selective scan backward, GENERIC path (shapes TMA cannot express: ragged rows, channel groups that are
+// not a multiple of 32; d_state <= 16).  Every Sigma call takes scan_op_bwd_tma.cu instead.
 // (reference: csrc/selective_scan/selective_scan.cpp:251-362, selective_scan_bwd_kernel.cuh:68-274).
+// fp16 / bf16 inputs and du / ddelta outputs are read / written natively.
 //
 // Two sweeps.  (1) The forward kernel re-runs with `hs` set and leaves the state at the start of every
 // 32-position tile in scratch (the reference recomputes from its 2048-chunk states `x`, bwd_kernel.cuh:114-116).
@@ -12,15 +14,29 @@
 // Thread mapping as the forward: LPC lanes per channel, SPT = 4 states per lane.
 #include <algorithm>
 
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
 #include "scan_core.cuh"
 
 namespace sigma {
 
 constexpr int BW_LT = 32, BW_LTP = 36, BW_DT = 32;
 
+template <typename T> __device__ __forceinline__ float gen_to_f32(T v);
+template <> __device__ __forceinline__ float gen_to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float gen_to_f32<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float gen_to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T gen_from_f32(float v);
+template <> __device__ __forceinline__ float gen_from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half gen_from_f32<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 gen_from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
 struct ScanBwdParams {
-  const float *u, *delta, *A, *B, *C, *D, *bias, *dout, *hs;
-  float *du, *ddelta, *dA, *dB, *dC, *dD, *dbias;
+  const void *u, *delta, *B, *C, *dout;   // element type T
+  const float *A, *D, *bias, *hs;
+  void *du, *ddelta;                      // element type T
+  float *dA, *dB, *dC, *dD, *dbias;
   int batch, dim, L, N, G, dpg, tiles_per_group, ntiles, softplus;
 };
 
@@ -31,8 +47,9 @@ __host__ __device__ constexpr int bwd_smem_floats() {
   return (3 * BW_DT + 2 * SPT * LPC) * BW_LTP + (2 * BW_DT + 2 * SPT * LPC) * BW_LTP + BW_LT * 32 * LPC * SPT;
 }
 
-template <int SPT, int LPC>
+template <typename T, int SPT, int LPC>
 __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdParams p) {
+  const T *pu = (const T *)p.u, *pdl = (const T *)p.delta, *pdo = (const T *)p.dout, *pB = (const T *)p.B, *pC = (const T *)p.C;
   constexpr int NP = SPT * LPC, CPW = 32 / LPC, NTH = 32 * LPC;
   extern __shared__ __align__(16) float smem[];
   float *sU = smem, *sDl = sU + BW_DT * BW_LTP, *sDo = sDl + BW_DT * BW_LTP;
@@ -72,11 +89,11 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdPara
       const int row = i >> 5, e = i & 31;
       float v = 0.f;
       if (e < npos) {
-        if (row < BW_DT) { if (row < nch) v = p.u[row0 + (long long)row * p.L + l0 + e]; }
-        else if (row < 2 * BW_DT) { if (row - BW_DT < nch) v = p.delta[row0 + (long long)(row - BW_DT) * p.L + l0 + e]; }
-        else if (row < 3 * BW_DT) { if (row - 2 * BW_DT < nch) v = p.dout[row0 + (long long)(row - 2 * BW_DT) * p.L + l0 + e]; }
-        else if (row < 3 * BW_DT + NP) { const int n = row - 3 * BW_DT; if (n < p.N) v = p.B[bc0 + (long long)n * p.L + l0 + e]; }
-        else { const int n = row - 3 * BW_DT - NP; if (n < p.N) v = p.C[bc0 + (long long)n * p.L + l0 + e]; }
+        if (row < BW_DT) { if (row < nch) v = gen_to_f32<T>(pu[row0 + (long long)row * p.L + l0 + e]); }
+        else if (row < 2 * BW_DT) { if (row - BW_DT < nch) v = gen_to_f32<T>(pdl[row0 + (long long)(row - BW_DT) * p.L + l0 + e]); }
+        else if (row < 3 * BW_DT) { if (row - 2 * BW_DT < nch) v = gen_to_f32<T>(pdo[row0 + (long long)(row - 2 * BW_DT) * p.L + l0 + e]); }
+        else if (row < 3 * BW_DT + NP) { const int n = row - 3 * BW_DT; if (n < p.N) v = gen_to_f32<T>(pB[bc0 + (long long)n * p.L + l0 + e]); }
+        else { const int n = row - 3 * BW_DT - NP; if (n < p.N) v = gen_to_f32<T>(pC[bc0 + (long long)n * p.L + l0 + e]); }
       }
       smem[row * BW_LTP + e] = v;
     }
@@ -157,8 +174,8 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdPara
     for (int i = tid; i < 2 * BW_DT * BW_LT; i += NTH) {
       const int which = i / (BW_DT * BW_LT), r = (i >> 5) % BW_DT, e = i & 31;
       if (r < nch && e < npos) {
-        float *dst = which ? p.ddelta : p.du;
-        dst[row0 + (long long)r * p.L + l0 + e] = (which ? sDd : sDu)[r * BW_LTP + e];
+        T *dst = (T *)(which ? p.ddelta : p.du);
+        dst[row0 + (long long)r * p.L + l0 + e] = gen_from_f32<T>((which ? sDd : sDu)[r * BW_LTP + e]);
       }
     }
     for (int i = tid; i < 2 * NP * BW_LT; i += NTH) {
@@ -182,15 +199,16 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdPara
 }
 
 int scan_op_npad(int N);
-int scan_op_fwd_f32_hs(const float *u, const float *delta, const float *A, const float *B, const float *C, const float *D,
-                       const float *bias, float *out, float *x, float *hs, int batch, int dim, int L, int N, int G,
-                       int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes, int force_split,
-                       cudaStream_t stream);
+template <typename T>
+int scan_op_fwd_generic(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                        const float *bias, void *out, float *x, float *hs, int batch, int dim, int L, int N, int G,
+                        int softplus, const sigma_scan_strides &s, void *ws, size_t ws_bytes, int force_split,
+                        cudaStream_t stream);
 
-template <int SPT, int LPC>
+template <typename T, int SPT, int LPC>
 static int launch_bwd(const ScanBwdParams &p, cudaStream_t stream) {
   const size_t smem = (size_t)bwd_smem_floats<SPT, LPC>() * sizeof(float);
-  auto kern = scan_op_bwd_kernel<SPT, LPC>;
+  auto kern = scan_op_bwd_kernel<T, SPT, LPC>;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(p.G * p.tiles_per_group, p.batch);
   kern<<<grid, 32 * LPC, smem, stream>>>(p);
@@ -198,28 +216,29 @@ static int launch_bwd(const ScanBwdParams &p, cudaStream_t stream) {
   return SIGMA_OK;
 }
 
-size_t scan_op_bwd_workspace_bytes(int batch, int dim, int L, int N) {
+size_t scan_op_bwd_workspace_bytes(int batch, int dim, int L, int N, int elem_bytes) {
   const size_t ntiles = (L + BW_LT - 1) / BW_LT;
   const size_t hs = (size_t)batch * dim * ntiles * scan_op_npad(N) * sizeof(float);
-  const size_t out = (size_t)batch * dim * L * sizeof(float);   // forward output of the recompute sweep (discarded)
+  const size_t out = (size_t)batch * dim * L * elem_bytes;   // forward output of the recompute sweep (discarded)
   return ((hs + 255) & ~(size_t)255) + ((out + 255) & ~(size_t)255);
 }
 
-// all tensors contiguous fp32
-int scan_op_bwd_f32(const float *u, const float *delta, const float *A, const float *B, const float *C, const float *D,
-                    const float *bias, const float *dout, float *du, float *ddelta, float *dA, float *dB, float *dC,
-                    float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
-                    size_t ws_bytes, cudaStream_t stream) {
-  if (N > 16) { set_error("sigma_scan_bwd: d_state=%d > 16 is not supported by the backward kernel", N); return SIGMA_EUNSUPPORTED; }
-  if (ws == nullptr || ws_bytes < scan_op_bwd_workspace_bytes(batch, dim, L, N)) {
-    set_error("sigma_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, scan_op_bwd_workspace_bytes(batch, dim, L, N));
+// all tensors contiguous, element type T
+template <typename T>
+int scan_op_bwd_generic(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
+                        const float *bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
+                        float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
+                        size_t ws_bytes, cudaStream_t stream) {
+  if (N > 16) { set_error("sigma_scan_bwd: d_state=%d > 16 is not supported by the backward kernels", N); return SIGMA_EUNSUPPORTED; }
+  if (ws == nullptr || ws_bytes < scan_op_bwd_workspace_bytes(batch, dim, L, N, (int)sizeof(T))) {
+    set_error("sigma_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, scan_op_bwd_workspace_bytes(batch, dim, L, N, (int)sizeof(T)));
     return SIGMA_EWORKSPACE;
   }
   const int NP = scan_op_npad(N);
   const int ntiles = (L + BW_LT - 1) / BW_LT;
   float *hs = (float *)ws;
   const size_t hs_b = (((size_t)batch * dim * ntiles * NP * sizeof(float)) + 255) & ~(size_t)255;
-  float *out_tmp = (float *)((char *)ws + hs_b);
+  void *out_tmp = (char *)ws + hs_b;
   sigma_scan_strides st;
   st.u_batch = st.delta_batch = st.out_batch = (int64_t)dim * L;
   st.u_dim = st.delta_dim = st.out_dim = L;
@@ -227,8 +246,8 @@ int scan_op_bwd_f32(const float *u, const float *delta, const float *A, const fl
   st.B_batch = st.C_batch = (int64_t)G * N * L;
   st.B_group = st.C_group = (int64_t)N * L;
   st.B_dstate = st.C_dstate = L;
-  int rc = scan_op_fwd_f32_hs(u, delta, A, B, C, D, bias, out_tmp, nullptr, hs, batch, dim, L, N, G, softplus, st, nullptr, 0, 1,
-                              stream);
+  int rc = scan_op_fwd_generic<T>(u, delta, A, B, C, D, bias, out_tmp, nullptr, hs, batch, dim, L, N, G, softplus, st, nullptr, 0,
+                                  1, stream);
   if (rc) return rc;
   SIGMA_CHECK_CUDA(cudaMemsetAsync(dA, 0, (size_t)dim * N * sizeof(float), stream));
   SIGMA_CHECK_CUDA(cudaMemsetAsync(dB, 0, (size_t)batch * G * N * L * sizeof(float), stream));
@@ -242,10 +261,19 @@ int scan_op_bwd_f32(const float *u, const float *delta, const float *A, const fl
   p.tiles_per_group = (p.dpg + BW_DT - 1) / BW_DT;
   p.ntiles = ntiles; p.softplus = softplus;
   switch (NP) {
-    case 4: return launch_bwd<4, 1>(p, stream);
-    case 8: return launch_bwd<4, 2>(p, stream);
-    default: return launch_bwd<4, 4>(p, stream);
+    case 4: return launch_bwd<T, 4, 1>(p, stream);
+    case 8: return launch_bwd<T, 4, 2>(p, stream);
+    default: return launch_bwd<T, 4, 4>(p, stream);
   }
 }
+
+#define SIGMA_INST(T)                                                                                                       \
+  template int scan_op_bwd_generic<T>(const void *, const void *, const float *, const void *, const void *, const float *, \
+                                      const float *, const void *, void *, void *, float *, float *, float *, float *,     \
+                                      float *, int, int, int, int, int, int, void *, size_t, cudaStream_t);
+SIGMA_INST(float)
+SIGMA_INST(__half)
+SIGMA_INST(__nv_bfloat16)
+#undef SIGMA_INST
 
 }  // namespace sigma

@@ -67,7 +67,7 @@ def selective_scan_cuda_core_fwd(u, delta, A, B, C, D=None, delta_bias=None, del
     dt = _DTYPE[u.dtype]
     wsb = L_.sigma_scan_fwd_workspace_bytes(batch, dim, L, N, G, dt)
     ws = torch.empty(wsb, dtype=torch.uint8, device=u.device)
-    if _force_split and dt == _lib.F32:
+    if _force_split and dt == _lib.F32:  # the split hook is fp32-only
         rc = L_.sigma_scan_fwd_f32_split(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias),
                                          _ptr(out), _ptr(x), batch, dim, L, N, G, int(bool(delta_softplus)),
                                          ctypes.byref(st), _ptr(ws), wsb, int(_force_split), _stream())
@@ -79,7 +79,7 @@ def selective_scan_cuda_core_fwd(u, delta, A, B, C, D=None, delta_bias=None, del
     return [out, x]
 
 
-def selective_scan_cuda_core_bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, nrows=1):
+def selective_scan_cuda_core_bwd(u, delta, A, B, C, D, delta_bias, dout, x, delta_softplus, nrows=1, _force_split=0):
     """Drop-in for selective_scan_cuda_core.bwd (selective_scan.cpp:251-362)
     -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]."""
     _require_cuda(u, delta, A, B, C, D, delta_bias, dout)
@@ -101,9 +101,14 @@ def selective_scan_cuda_core_bwd(u, delta, A, B, C, D, delta_bias, dout, x, delt
     dt = _DTYPE[u.dtype]
     wsb = L_.sigma_scan_bwd_workspace_bytes(batch, dim, L, N, G, dt)
     ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=u.device)
-    rc = L_.sigma_scan_bwd(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias), _ptr(dout),
-                           _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias),
-                           batch, dim, L, N, G, dt, int(bool(delta_softplus)), _ptr(ws), wsb, _stream())
+    if _force_split:
+        rc = L_.sigma_scan_bwd_split(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias), _ptr(dout),
+                                     _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias),
+                                     batch, dim, L, N, G, dt, int(bool(delta_softplus)), _ptr(ws), wsb, int(_force_split), _stream())
+    else:
+        rc = L_.sigma_scan_bwd(_ptr(u), _ptr(delta), _ptr(A), _ptr(B), _ptr(C), _ptr(D), _ptr(delta_bias), _ptr(dout),
+                               _ptr(du), _ptr(ddelta), _ptr(dA), _ptr(dB), _ptr(dC), _ptr(dD), _ptr(dbias),
+                               batch, dim, L, N, G, dt, int(bool(delta_softplus)), _ptr(ws), wsb, _stream())
     _lib.check(rc, "sigma_scan_bwd")
     # the reference returns dB/dC cast to the input dtype (selective_scan.cpp:360)
     return [du, ddelta, dA, dB.to(u.dtype), dC.to(u.dtype), dD, dbias]

@@ -33,3 +33,12 @@ def assert_close(a, b, rtol, atol, what=""):
     bad = err > tol
     assert not bad.any(), (f"{what}: {bad.sum()}/{bad.size} elements out of tolerance; max abs err {err.max():.3e} "
                            f"(|ref| max {np.abs(b).max():.3e}), rtol={rtol} atol={atol}")
+
+
+def record(name, **kv):
+    """Append one JSON line of measured parity numbers to $SIGMA_PARITY_LOG (set by the GPU run scripts)."""
+    import json
+    path = os.environ.get("SIGMA_PARITY_LOG")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps(dict(test=name, **kv)) + "\n")

@@ -15,7 +15,7 @@ import pytest
 import torch
 
 import procedural as P
-from helpers import SEED, cfg_tiny, golden
+from helpers import SEED, cfg_tiny, golden, record
 from oracle import sigma_ref
 
 pytestmark = pytest.mark.gpu
@@ -84,7 +84,7 @@ def test_logits_vs_reference_golden_fullsize(which, path):
     else:
         bar, agree, mtol = fused.logits_bar(), 0.995, 2e-3
     e, a = _check(logits, g, ncls, tag, bar, agree, mtol, H, W)
-    print(f"[fullsize golden] {tag} {path}: logits err {e:.2e} of scale, labels equal {a:.5f}")
+    record("fullsize_golden", tag=tag, path=path, precision=fused.PRECISION, logits_err_of_scale=e, labels_equal=a)
     # the encoder maps too (fused path returns NCHW views like the reference)
     with torch.no_grad(), M.composed_path(path == "composed"):
         feats = model.backbone(rgb, mx)
@@ -113,6 +113,6 @@ def test_fused_vs_oracle_port_480x640_b2():
     scale = float(ref.abs().max())
     err = float((got - ref).abs().max())
     agree = float((got.argmax(1) == ref.argmax(1)).float().mean())
-    print(f"[fullsize oracle] fused vs oracle port: err {err / scale:.2e} of scale, labels equal {agree:.5f}")
+    record("fullsize_oracle_b2", precision=fused.PRECISION, logits_err_of_scale=err / scale, labels_equal=agree)
     assert err <= fused.logits_bar() * scale, f"logits differ by {err:.3e} ({err / scale:.2e} of scale)"
     assert agree >= 0.995

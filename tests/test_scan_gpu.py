@@ -90,8 +90,8 @@ def test_fwd_strided_inputs_and_x_states():
             h = scan_oracle.scan_fwd(u[:, :, :lend].numpy(), dl[:, :, :lend].numpy(), A.numpy(), Bm[..., :lend].numpy(),
                                      Csel[..., :lend].numpy(), None, bias.numpy(), True)[:, :, -1]
             assert_close(x[:, :, c, 2 * s + 1], h, 6e-4, 2e-3, f"x.h chunk{c} state{s}")
-        l0 = c * 2048
-        dls = torch.nn.functional.softplus(dl[:, :, l0:lend] + bias[None, :, None]).double().sum(-1)
+        # running prefix since the SEQUENCE start (SSMScanPrefixCallbackOp, fwd_kernel.cuh:181-184), not per chunk
+        dls = torch.nn.functional.softplus(dl[:, :, :lend] + bias[None, :, None]).double().sum(-1)
         prod_a = torch.exp(dls[..., None] * A.double()[None])
         assert_close(x[:, :, c, 0::2], prod_a.float(), 2e-3, 1e-6, f"x.prod_a chunk{c}")
 
@@ -105,3 +105,37 @@ def test_errors_are_loud():
         ops.selective_scan_cuda_core_fwd(u, u, A, Bm, Bm, None, None, False, 1)
     with pytest.raises(RuntimeError):                     # CPU tensors: no fallback
         ops.selective_scan_cuda_core_fwd(u.cpu(), u.cpu(), A.cpu(), Bm.cpu(), Bm.cpu(), None, None, False, 1)
+
+
+@pytest.mark.parametrize("b,d,n,L,G", [(2, 64, 16, 300, 2), (1, 192, 16, 4800, 1), (3, 96, 4, 1204, 3), (1, 256, 8, 2400, 4),
+                                       (2, 768, 16, 1200, 4), (1, 128, 4, 4500, 1)])
+@pytest.mark.parametrize("dn", ["f32", "bf16", "f16"])
+def test_fwd_tma_path(b, d, n, L, G, dn):
+    """Shapes the TMA-staged kernel takes (channel groups % 32 == 0, 16-byte rows): all element types natively, 1 / 3 / 7
+    L-segments, chunk states with the running prefix, and agreement with the generic kernel (SIGMA_OP_GENERIC)."""
+    import os
+    from sigma_b200 import ops
+    dt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[dn]
+    if dn != "f32" and L % 8:
+        L = L - L % 8
+    u, dl, A, Bm, Cm, D, bias = P.scan_inputs(SEED + 9, b, d, n, L, G)
+    q = lambda t: t.to(dt)
+    f = lambda t: q(t).float().numpy()
+    ref = scan_oracle.scan_fwd(f(u), f(dl), A.numpy(), f(Bm), f(Cm), D.numpy(), bias.numpy(), True)
+    rt, at = (6e-4, 2e-3) if dn == "f32" else ((3e-3, 5e-3) if dn == "f16" else (3e-2, 5e-2))
+    args = (q(u).cuda(), q(dl).cuda(), A.cuda(), q(Bm).cuda(), q(Cm).cuda(), D.cuda(), bias.cuda(), True, 1)
+    out, x = ops.selective_scan_cuda_core_fwd(*args)
+    assert out.dtype == dt
+    assert_close(out, ref, rt, at, f"tma {dn} {(b, d, n, L, G)}")
+    if dn == "f32":
+        for split in (3, 7):
+            o2, x2 = ops.selective_scan_cuda_core_fwd(*args, _force_split=split)
+            assert_close(o2, ref, rt, at, f"tma split={split}")
+            assert_close(x2, x.cpu().numpy(), 2e-3, 1e-5, f"x states split={split}")
+    os.environ["SIGMA_OP_GENERIC"] = "1"
+    try:
+        og, xg = ops.selective_scan_cuda_core_fwd(*args)
+    finally:
+        del os.environ["SIGMA_OP_GENERIC"]
+    assert_close(out, og.float().cpu().numpy(), rt, at, "tma vs generic kernel")
+    assert_close(x, xg.cpu().numpy(), 2e-3, 1e-5, "x states tma vs generic")
