@@ -119,7 +119,10 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdPara
       }
     }
 
-    // ---- reverse recurrence ----
+    // ---- reverse recurrence (dA: per-tile partial sums folded into the running total — two-level summation) ----
+    float dAt[SPT];
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) dAt[s] = 0.f;
     for (int i = npos - 1; i >= 0; --i) {
       const float raw = sDl[c_local * BW_LTP + i] + bias;
       const float dl = p.softplus ? softplus20(raw) : raw;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdPara
         cC[s] = dy * hi;                              // dC contribution (:225)
         const float da = dh[s] * hprev;               // d/da of a·h_{i-1}
         ddl = fmaf(da * a, Araw[s], fmaf(dh[s] * Bn, ui, ddl));   // (:206)
-        dAacc[s] = fmaf(da * a, dl, dAacc[s]);        // (:208)
+        dAt[s] = fmaf(da * a, dl, dAt[s]);            // (:208)
         cB[s] = dh[s] * dl * ui;                      // dB contribution (:224)
         dui = fmaf(dh[s] * dl, Bn, dui);              // (:205)
         dh[s] *= a;
@@ -169,6 +172,8 @@ __global__ void __launch_bounds__(32 * LPC) scan_op_bwd_kernel(const ScanBwdPara
         sDd[c_local * BW_LTP + i] = ddl;
       }
     }
+#pragma unroll
+    for (int s = 0; s < SPT; ++s) dAacc[s] += dAt[s];
     __syncthreads();
     // ---- write the tile: du, ddelta rows; dB/dC: one atomic per (n, l) per CTA ----
     for (int i = tid; i < 2 * BW_DT * BW_LT; i += NTH) {

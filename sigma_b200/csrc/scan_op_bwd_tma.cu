@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(128, 2) scan_op_bwd_tma_kernel(const __grid_co
       }
     }
 
-    // ---- reverse recurrence, groups of 4 positions from the end of the tile ----
+    // ---- reverse recurrence, groups of 4 positions from the end of the sub-tile ----
+    float dAt[NS];   // dA of this sub-tile, folded into the running total below (two-level summation over L)
+#pragma unroll
+    for (int s = 0; s < NS; ++s) dAt[s] = 0.f;
 #pragma unroll 1
     for (int gi = ng - 1; gi >= 0; --gi) {
       float raw[G], uu[G], dy[G];
@@ -233,8 +236,8 @@ __global__ void __launch_bounds__(128, 2) scan_op_bwd_tma_kernel(const __grid_co
             const f2 t = mul2(dhn, ahp);
             s1 = fma2(dhn, Bp, s1);
             s2 = fma2(t, f2{a2[s], a2[s + 1]}, s2);
-            const f2 da = fma2(t, f2{dl, dl}, f2{dAacc[s], dAacc[s + 1]});     // (:208)
-            dAacc[s] = da.x; dAacc[s + 1] = da.y;
+            const f2 da = fma2(t, f2{dl, dl}, f2{dAt[s], dAt[s + 1]});         // (:208)
+            dAt[s] = da.x; dAt[s + 1] = da.y;
             const f2 cb = mul2(dhn, f2{dlu, dlu});                             // dB term (:224)
             const f2 dhm = mul2(dhn, a);
             dh[s] = dhm.x; dh[s + 1] = dhm.y;
@@ -270,8 +273,12 @@ __global__ void __launch_bounds__(128, 2) scan_op_bwd_tma_kernel(const __grid_co
         red_add_v4(dCg + off, rC[0], rC[1], rC[2], rC[3]);
       }
     }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) dAacc[s] += dAt[s];
     }   // sub-tiles
 
+    // this warp's rows of du / ddelta -> global; the slot may be refilled once the stores have READ it (a tile of the
+    // backward is ~4x the forward's work, so the wait is small against it and the ring stays at 2 stages)
     fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
@@ -279,12 +286,12 @@ __global__ void __launch_bounds__(128, 2) scan_op_bwd_tma_kernel(const __grid_co
       tma_store_3d(&p.m_dd, sDl + warp * CPW * OPT_ROW_BYTES, tau * LT, d0 + warp * CPW, b);
       tma_store_commit();
       tma_store_wait_read<0>();
+      if (k + NST < ntl) {
+        const uint32_t old = smem_inc_acq_rel(&done[st]);
+        if ((old + 1) % (uint32_t)nwarps == 0) request_tile(k + NST, st);
+      }
     }
     __syncwarp();
-    if (lane == 0 && k + NST < ntl) {
-      const uint32_t old = smem_inc_acq_rel(&done[st]);
-      if ((old + 1) % (uint32_t)nwarps == 0) request_tile(k + NST, st);
-    }
     if (++st == NST) { st = 0; ph ^= 1; }
   }
   if (lane == 0) tma_store_wait_all<0>();
@@ -424,11 +431,7 @@ size_t scan_op_bwd_tma_workspace_bytes(int batch, int dim, int L, int N, int ele
 template <typename T, int NP>
 static int launch_bwd_tma(ScanBwdTmaParams &p, cudaStream_t stream) {
   constexpr int LPC = BwdCfg<NP>::LPC;
-  auto prep = [&](const void *fn, size_t smem) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  };
+  auto prep = [&](const void *fn, size_t smem) -> cudaError_t { (void)smem; return prep_kernel_once(fn); };
   dim3 grid(p.G * p.ctiles_per_group, p.nsplit, p.batch);
   if (p.nsplit > 1) {
     const size_t smem = 1024 + (size_t)p.nst * (2 * p.DT * OPT_ROW_BYTES + 2 * NP * OPT_ROW_BYTES) +

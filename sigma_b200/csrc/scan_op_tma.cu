@@ -15,6 +15,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
+#include <unordered_set>
 
 #include "scan_op_tma.cuh"
 
@@ -43,6 +45,20 @@ int make_tmap_generic(CUtensorMap *map, CUtensorMapDataType dtype, int rank, con
     return SIGMA_ECUDA;
   }
   return SIGMA_OK;
+}
+
+// Opt a kernel into the full 227 KB of dynamic shared memory, once per kernel and process (cudaFuncSetAttribute on every
+// call was a measurable part of the small-batch launch floor).
+cudaError_t prep_kernel_once(const void *fn) {
+  static std::mutex mu;
+  static std::unordered_set<const void *> seen;
+  std::lock_guard<std::mutex> lk(mu);
+  if (seen.count(fn)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e == cudaSuccess) seen.insert(fn);
+  return e;
 }
 
 struct alignas(64) ScanTmaParams {
@@ -123,17 +139,16 @@ __global__ void __launch_bounds__(128, OpCfg<NP>::CTAS) scan_op_tma_kernel(const
   const float Dv = p.D ? p.D[d] : 0.f;
   const bool sp = p.softplus != 0;
   float sumdl = 0.f;      // Σ delta' over this CTA's walk (running prefix of the chunk states; segment product in MODE_SUMMARY)
-  float *carry_row = nullptr;
-  if (MODE != MODE_SERIAL) {
-    carry_row = p.carry + (((long long)b * p.dim + d) * p.nsplit + split) * 2 * NP;
-    if (MODE == MODE_APPLY) {
+  // (prod a, h) of this CTA's L-segment: written by MODE_SUMMARY, chained by the combine kernel, read by MODE_APPLY
+  auto carry_row = [&]() { return p.carry + (((long long)b * p.dim + d) * p.nsplit + split) * 2 * NP; };
+  if (MODE == MODE_APPLY) {
+    const float *cr = carry_row();
 #pragma unroll
-      for (int s = 0; s < NP; ++s) h[s] = carry_row[NP + s];
-    }
+    for (int s = 0; s < NP; ++s) h[s] = cr[NP + s];
   }
   float *bct = bct_all + warp * op_bct_floats<T, NP>();
 
-  int st = 0, ph = 0;
+  int st = 0, ph = 0, pst = 0;
   for (int tau = t0; tau < t1; ++tau) {
     mbar_spin(&full[st], (uint32_t)ph);
     unsigned char *sU = smem + (size_t)st * stage_b;
@@ -231,36 +246,48 @@ __global__ void __launch_bounds__(128, OpCfg<NP>::CTAS) scan_op_tma_kernel(const
           for (int s = 0; s < NP; ++s) {
             if (s < p.N) {
               float P = ex2(a2[s] * sumdl);
-              if (MODE == MODE_APPLY) P *= carry_row[s];   // product over the preceding segments
+              if (MODE == MODE_APPLY) P *= carry_row()[s];   // product over the preceding segments
               xr[2 * s] = P;
               xr[2 * s + 1] = h[s];
             }
           }
         }
       }
-      // this warp's 32 rows of y -> global: generic-proxy writes made visible to the async proxy, one TMA store
+      // this warp's 32 rows of y -> global: generic-proxy writes made visible to the async proxy, one TMA store.  The
+      // slot is released one tile LATER (when at most one store group is still reading shared memory): nobody waits for
+      // a TMA store, the ring is one stage deeper instead.
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         tma_store_3d(&p.m_out, sU + warp * 32 * OPT_ROW_BYTES, tau * LT, d0 + warp * 32, b);
         tma_store_commit();
-        tma_store_wait_read<0>();   // the slot may be refilled once the store has READ it
+        if (tau > t0) {
+          tma_store_wait_read<1>();
+          if (tau - 1 + NST < t1) {
+            const uint32_t old = smem_inc_acq_rel(&done[pst]);
+            if ((old + 1) % (uint32_t)nwarps == 0) request_tile(tau - 1 + NST, pst);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      __syncwarp();
+      if (lane == 0 && tau + NST < t1) {
+        const uint32_t old = smem_inc_acq_rel(&done[st]);
+        if ((old + 1) % (uint32_t)nwarps == 0) request_tile(tau + NST, st);
       }
     }
-    __syncwarp();
-    if (lane == 0 && tau + NST < t1) {
-      const uint32_t old = smem_inc_acq_rel(&done[st]);
-      if ((old + 1) % (uint32_t)nwarps == 0) request_tile(tau + NST, st);
-    }
+    pst = st;
     if (++st == NST) { st = 0; ph ^= 1; }
   }
   if (WITH_Y && lane == 0) tma_store_wait_all<0>();
 
   if (MODE == MODE_SUMMARY) {
+    float *cr = carry_row();
 #pragma unroll
     for (int s = 0; s < NP; ++s) {
-      carry_row[s] = ex2(a2[s] * sumdl);
-      carry_row[NP + s] = h[s];
+      cr[s] = ex2(a2[s] * sumdl);
+      cr[NP + s] = h[s];
     }
   }
 }
@@ -295,11 +322,7 @@ template <typename T, int NP>
 static int launch_tma(ScanTmaParams &p, bool yout, cudaStream_t stream) {
   const size_t smem = op_tma_smem_bytes<T, NP>(p.DT, p.nst);
   dim3 grid(p.G * p.ctiles_per_group, p.nsplit, p.batch), block(p.DT);
-  auto prep = [&](const void *fn) -> cudaError_t {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  };
+  auto prep = [&](const void *fn) -> cudaError_t { return prep_kernel_once(fn); };
   auto run = [&](auto kern) -> int {
     SIGMA_CHECK_CUDA(prep((const void *)kern));
     kern<<<grid, block, smem, stream>>>(p);
@@ -358,8 +381,8 @@ int scan_op_fwd_tma(const void *u, const void *delta, const float *A, const void
     const size_t stage = (size_t)2 * p.DT * OPT_ROW_BYTES + (size_t)2 * NP * OPT_ROW_BYTES;
     const size_t fixed = 1024 + 256 + (size_t)nw * LT * (2 * NP + 4) * sizeof(float);
     int nst = budget > fixed ? (int)((budget - fixed) / stage) : 2;
-    p.nst = std::max(2, std::min(8, nst));
-    if (const char *e = getenv("SIGMA_OP_NST")) p.nst = std::max(2, std::min(8, atoi(e)));
+    p.nst = std::max(3, std::min(8, nst));   // >= 3: a slot is released one tile after its last use
+    if (const char *e = getenv("SIGMA_OP_NST")) p.nst = std::max(3, std::min(8, atoi(e)));
   }
 
   const uint64_t sz = sizeof(T);

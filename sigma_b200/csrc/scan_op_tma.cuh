@@ -117,6 +117,8 @@ __device__ __forceinline__ void transpose_bc(const unsigned char *rawB, const un
 int make_tmap_generic(CUtensorMap *map, CUtensorMapDataType dtype, int rank, const void *base, const uint64_t *dims,
                       const uint64_t *strides_bytes, const uint32_t *box, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo);
 
+cudaError_t prep_kernel_once(const void *fn);   // scan_op_tma.cu
+
 // global <- shared, 3-D box (per-warp y / gradient rows)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map),

@@ -74,23 +74,6 @@ struct Ss2dThread {
   int ablate;
 };
 
-// 2^x for x <= 0 on the FMA / ALU pipes instead of the SFU: round to the nearest integer with the 1.5·2^23 trick,
-// degree-5 polynomial for 2^f on [-0.5, 0.5], exponent added to the bit pattern.  Max relative error 2.4e-7 in fp32
-// (numpy sweep over [-120, 0]) — the level of MUFU.EX2.  EXPERIMENTAL (round 2): only the kernels built
-// with NPOLY > 0 use it (ss2d_scan_poly.cu, selected by SIGMA_SCAN_POLY); the default kernels do not.
-__device__ __forceinline__ float ex2_poly(float x) {
-  x = fmaxf(x, -125.f);                                  // keep the exponent field in range; 2^-125 ~ 0
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float p = 0.0013390863314270973f;
-  p = fmaf(p, f, 0.009676031768321991f);
-  p = fmaf(p, f, 0.055503569543361664f);
-  p = fmaf(p, f, 0.2402210682630539f);
-  p = fmaf(p, f, 0.6931471824645996f);
-  p = fmaf(p, f, 1.0000001192092896f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-
 // packed helpers on raw 64-bit register pairs (keep loop-invariant pairs paired: no MOVs to rebuild them)
 __device__ __forceinline__ unsigned long long fma2_raw(unsigned long long a, unsigned long long b, unsigned long long c) {
   unsigned long long d;
@@ -150,7 +133,7 @@ __device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, 
 // position (this thread's first channel), `ystride` = y elements between consecutive positions.
 // Per position B and C are read ONCE (2·N/4 broadcast LDS.128) and reused by the CPT channels of the thread;
 // per channel and state pair: FMUL2 (exp arguments), 2 x MUFU.EX2, FMUL2 (delta·u·B), FFMA2 (h), FFMA2 (C·h).
-template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL, int NPOLY = 0>
+template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL>
 __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *rb, const float *rc, float *yp,
                                            long long ystride, int ycstride, const float (&dl)[CPT][G],
                                            const float (&u)[CPT][G], int cnt) {
@@ -175,8 +158,7 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
           for (int hp = 0; hp < 2; ++hp) {                                   // state pair (4·s4 + 2·hp, +1)
             const int s = 4 * s4 + 2 * hp;
             const f2 arg = mul2(f2{d, d}, f2{t.a2[c][s], t.a2[c][s + 1]});
-            // NPOLY state pairs per position take their exponentials from the FMA pipe (experimental, default 0)
-            const f2 a = (NPOLY > 0 && s < 2 * NPOLY) ? f2{ex2_poly(arg.x), ex2_poly(arg.y)} : f2{ex2(arg.x), ex2(arg.y)};
+            const f2 a = f2{ex2(arg.x), ex2(arg.y)};
             const f2 bb = mul2(f2{du, du}, hp == 0 ? f2{bv.x, bv.y} : f2{bv.z, bv.w});
             const f2 hn = fma2(a, f2{t.h[c][s], t.h[c][s + 1]}, bb);
             t.h[c][s] = hn.x; t.h[c][s + 1] = hn.y;
@@ -220,7 +202,7 @@ struct Ss2dWalk {
 // The tile loop of one warp.  The software pipeline over groups of G positions runs ACROSS tiles: while the
 // recurrence of group g runs, delta'/u of group g+1 are computed — from the next tile's ring slot when g is the
 // last group of its tile — so no prologue is exposed at a tile boundary and none is computed twice.
-template <int N, int CPT, int RP, bool WITH_Y, bool REV, int NPOLY, typename Request>
+template <int N, int CPT, int RP, bool WITH_Y, bool REV, typename Request>
 __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2dWalk<N, CPT, RP> &w, Request &&request_tile) {
   constexpr int G = Ss2dCfg<N>::G, LT = Ss2dCfg<N>::LT;
   constexpr int Cp = 2 * N + RP;
@@ -290,10 +272,10 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
 #pragma unroll
             for (int i = 0; i < G; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
         }
-        group_body<N, CPT, RP, G, WITH_Y, REV, true, NPOLY>(t, rb, rc, yp, w.istride, ycs, dl, u, G);
+        group_body<N, CPT, RP, G, WITH_Y, REV, true>(t, rb, rc, yp, w.istride, ycs, dl, u, G);
       } else {
         group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
-        group_body<N, CPT, RP, G, WITH_Y, REV, false, NPOLY>(t, rb, rc, yp, w.istride, ycs, dl, u, cnt);
+        group_body<N, CPT, RP, G, WITH_Y, REV, false>(t, rb, rc, yp, w.istride, ycs, dl, u, cnt);
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
@@ -312,7 +294,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
   }
 }
 
-template <int N, int CPT, int RP, int MODE, int NPOLY = 0>
+template <int N, int CPT, int RP, int MODE>
 __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
@@ -412,8 +394,8 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
   w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I; w.nst = NST;
   w.cross = cross; w.rev = rev;
 
-  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true, NPOLY>(t, w, request_tile);
-  else     walk_tiles<N, CPT, RP, WITH_Y, false, NPOLY>(t, w, request_tile);
+  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true>(t, w, request_tile);
+  else     walk_tiles<N, CPT, RP, WITH_Y, false>(t, w, request_tile);
 
   if (MODE == MODE_SUMMARY || SIGMA_ABL(p.ablate, 1)) {
 #pragma unroll
@@ -431,7 +413,7 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
 
 // host-side launcher for one (N, CPT, RP) instantiation; defined per RP in ss2d_scan_rp*.cu.
 // `nthreads` = threads per CTA (each owning CPT channels).
-template <int N, int CPT, int RP, int NPOLY = 0>
+template <int N, int CPT, int RP>
 int ss2d_launch(const Ss2dParams &p, int nthreads, cudaStream_t stream);
 
 }  // namespace sigma

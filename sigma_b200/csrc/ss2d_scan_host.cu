@@ -175,22 +175,6 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
     if (const char *e = getenv("SIGMA_SCAN_NST")) p.nst = std::max(2, std::min(Ss2dCfg<16>::MAX_NST, atoi(e)));
   }
   const int nthreads = 32 * NW;
-  // EXPERIMENTAL, off unless SIGMA_SCAN_POLY=<1..3>: polynomial exp2 for that many of the 8 state pairs (ss2d_scan_poly_rp*.cu)
-  if (N == 16) {
-    static const int poly = [] { const char *e = getenv("SIGMA_SCAN_POLY"); return e ? atoi(e) : 0; }();
-#define SIGMA_POLY_CASE(RPV)                                                         \
-    case RPV:                                                                          \
-      if (poly == 1) return ss2d_launch<16, 1, RPV, 1>(p, nthreads, stream);           \
-      if (poly == 2) return ss2d_launch<16, 1, RPV, 2>(p, nthreads, stream);           \
-      if (poly == 3) return ss2d_launch<16, 1, RPV, 3>(p, nthreads, stream);           \
-      break;
-    if (poly > 0) {
-      switch (pad_rp(p.R)) {
-        SIGMA_POLY_CASE(8) SIGMA_POLY_CASE(12) SIGMA_POLY_CASE(24) SIGMA_POLY_CASE(48)
-      }
-    }
-#undef SIGMA_POLY_CASE
-  }
   switch (N) {
     case 4: return dispatch_rp<4, 1>(p, nthreads, stream);
     case 8: return dispatch_rp<8, 1>(p, nthreads, stream);
