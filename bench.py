@@ -34,11 +34,15 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=74,
+    ap.add_argument("--batch", type=int, default=None,
                     help="images per GPU per step.  74 = 2 x 37: the encoder scans' grids (16 / 24 / 48 / 96 CTAs per image) are then "
                          "whole multiples of the 592 / 444 resident CTA slots of the 148 SMs (measured: 32 -> 337, 37 -> 358, "
                          "74 -> 374, 111 -> 376 images/s); 49 GB of the 180 GB HBM")
     ap.add_argument("--impl", default="sigma", choices=["sigma", "reference"])
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="train: one step = forward + CE loss + backward + AdamW (train.py:164-172), torch DDP over NCCL when N > 1 "
+                         "(BASELINE configs 3 / 4); default batch 2 per GPU")
+    ap.add_argument("--amp", default="none", choices=["none", "bf16"], help="train mode: autocast dtype of the dense layers")
     ap.add_argument("--model", default="sigma_tiny")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -47,7 +51,10 @@ def parse():
     ap.add_argument("--cublas-gemm", action="store_true", help="A/B: dense projections through cuBLAS instead of our tcgen05 GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-images", type=int, default=2)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.batch is None:
+        a.batch = 74 if a.mode == "infer" else 2
+    return a
 
 
 def cfg_of(a):
@@ -231,11 +238,162 @@ def measure_roofline(model, rgb, mx, reps=3):
     return tot_b, tot_ms, len(calls), 1, by_n
 
 
+
+# ------------------------------------------------------------------ training arm (BASELINE configs 3 and 4)
+def scan_algo_bytes_op(batch, dim, L, N, G, elem, bwd):
+    """Algorithmic bytes of one op-level scan call (SURVEY.md §8d formula; backward: u, delta, B, C, dout read, du, ddelta,
+    dB, dC written (dB / dC fp32), A / D / bias read, dA / dD / dbias written)."""
+    if not bwd:
+        return elem * (3 * batch * dim * L + 2 * batch * G * N * L) + 4 * (dim * N + 2 * dim)
+    return elem * (5 * batch * dim * L + 2 * batch * G * N * L) + 4 * 2 * batch * G * N * L + 4 * 2 * (dim * N + 2 * dim)
+
+
+def run_train(a):
+    import contextlib
+    import io
+    import torch.distributed as dist
+    from sigma_b200 import _lib, dist_util, modules as M, ops, train_util
+    world, rank, local = dist_util.env_world()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_util.init("nccl", dev)
+    torch.backends.cuda.matmul.allow_tf32 = True      # dense layers of the training path: cuBLAS / cuDNN TF32 (or bf16 autocast)
+    torch.backends.cudnn.allow_tf32 = True
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.EncoderDecoder(cfg_of(a), criterion=torch.nn.CrossEntropyLoss(reduction="mean", ignore_index=255)).to(dev).train()
+    opt = train_util.make_optimizer(model)
+    ddp = train_util.wrap_ddp(model, local)
+    step_fn = train_util.TrainStep(ddp, opt, amp_dtype=torch.bfloat16 if a.amp == "bf16" else None)
+    B = a.batch
+    g = torch.Generator().manual_seed(dist_util.shard_seed(1234, rank))
+    h_rgb = torch.randn(B, 3, a.height, a.width, generator=g).pin_memory()
+    h_mx = torch.randn(B, 3, a.height, a.width, generator=g).pin_memory()
+    h_gt = torch.randint(0, a.num_classes, (B, a.height, a.width), generator=g, dtype=torch.int64).pin_memory()
+    rgb, mx, gt = h_rgb.to(dev), h_mx.to(dev), h_gt.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step_fn(rgb, mx, gt)
+    barrier()
+    n0 = _lib.launch_count()
+    step_fn(rgb, mx, gt)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - n0
+
+    def timed(fn):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+        barrier()
+        for e0, e1 in ev:
+            flush.zero_()
+            e0.record()
+            fn()
+            e1.record()
+        barrier()
+        return dist_util.max_over_ranks(sum(e0.elapsed_time(e1) for e0, e1 in ev), dev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    total_ms = timed(lambda: step_fn(rgb, mx, gt))                      # inputs resident
+    nosync_ms = timed(lambda: step_fn(rgb, mx, gt, sync=False)) if world > 1 else total_ms   # the same step without the exchange
+
+    loss_host = torch.zeros(1).pin_memory()
+
+    def e2e_step():                                                      # the call train.py makes: host batch in, loss out
+        l = step_fn(h_rgb.to(dev, non_blocking=True), h_mx.to(dev, non_blocking=True), h_gt.to(dev, non_blocking=True))
+        loss_host.copy_(l.detach().reshape(1), non_blocking=True)
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step)
+    clocks = sampler.stop() if sampler else None
+    ar_s, ar_bw = train_util.allreduce_bus_bandwidth(train_util.grad_bytes(model), dev) if world > 1 else (0.0, None)
+
+    # ---- roofline of the dominant kernels: every op-level scan call (forward and backward) of one step, bracketed by events
+    rec = []
+    f0, b0 = ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd
+
+    def fwd_rec(u, delta, A, Bm, Cm, *r, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = f0(u, delta, A, Bm, Cm, *r, **k)
+        e1.record()
+        rec.append((False, e0, e1, scan_algo_bytes_op(u.shape[0], u.shape[1], u.shape[2], A.shape[1], Bm.shape[1], u.element_size(), False)))
+        return out
+
+    def bwd_rec(u, delta, A, Bm, Cm, *r, **k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = b0(u, delta, A, Bm, Cm, *r, **k)
+        e1.record()
+        rec.append((True, e0, e1, scan_algo_bytes_op(u.shape[0], u.shape[1], u.shape[2], A.shape[1], Bm.shape[1], u.element_size(), True)))
+        return out
+
+    ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = fwd_rec, bwd_rec
+    try:
+        step_fn(rgb, mx, gt, sync=False)
+        torch.cuda.synchronize()
+    finally:
+        ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = f0, b0
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    agg = {False: [0, 0.0, 0], True: [0, 0.0, 0]}
+    for is_bwd, e0, e1, nb in rec:
+        agg[is_bwd][0] += nb
+        agg[is_bwd][1] += e0.elapsed_time(e1)
+        agg[is_bwd][2] += 1
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    tot_b, tot_ms = agg[False][0] + agg[True][0], agg[False][1] + agg[True][1]
+    roofline = {"bound": "hbm", "kernel": "scan_op_tma_kernel + scan_op_bwd_tma_kernel (op-level selective scan, forward and backward)",
+                "achieved": round(tot_b / (tot_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(tot_b / (tot_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "note": "event-bracketed eager calls (host launch gaps included: an upper bound on kernel time)",
+                "fwd": {"calls": agg[False][2], "ms_per_step": round(agg[False][1], 3), "GBps": round(agg[False][0] / max(agg[False][1], 1e-9) / 1e6, 1)},
+                "bwd": {"calls": agg[True][2], "ms_per_step": round(agg[True][1], 3), "GBps": round(agg[True][0] / max(agg[True][1], 1e-9) / 1e6, 1)}}
+    n_img = B * world * a.steps
+    gb = train_util.grad_bytes(model)
+    in_bytes = h_rgb.numel() * 4 + h_mx.numel() * 4 + h_gt.numel() * 8
+    line = {
+        "metric": f"images/sec {a.model} {a.height}x{a.width} training step (fwd + bwd + AdamW)",
+        "value": round(n_img / (total_ms * 1e-3), 3), "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": round(total_ms / a.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 autocast dense + f32 scan" if a.amp == "bf16" else "f32 (tf32 dense)", "data": "synthetic",
+        "config": {"workload": f"{a.model} train step, synthetic RGB-X {a.height}x{a.width}, {a.num_classes} classes, CE loss, AdamW lr 6e-5 wd 0.01",
+                   "batch_per_gpu": B, "global_batch": B * world,
+                   "parallelism": f"DDP x{world} (NCCL all-reduce of {gb / 1e6:.0f} MB fp32 gradients per step)" if world > 1 else "single GPU",
+                   "path": "composed (torch autograd over sigma_scan_fwd / sigma_scan_bwd)", "l2": "256 MiB flush between timed steps",
+                   "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
+        "roofline": roofline, "cpu_baseline": None,
+        "collective": {"grad_bytes": gb, "allreduce_ms": round(ar_s * 1e3, 3), "bus_GBps": None if ar_bw is None else round(ar_bw, 1),
+                       "step_ms_with_exchange": round(total_ms / a.steps, 3), "step_ms_without_exchange": round(nosync_ms / a.steps, 3),
+                       "exposed_ms": round((total_ms - nosync_ms) / a.steps, 3),
+                       "overlap_frac": None if world == 1 or ar_s == 0 else round(max(0.0, 1.0 - ((total_ms - nosync_ms) / a.steps) / (ar_s * 1e3)), 3)},
+        "e2e": {"value": round(n_img / (e2e_ms * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
+                "mode": "pinned host batch -> device, step, loss read back, one stream"},
+        "gpu_launches": int(launches_per_step) * a.steps, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
 # ------------------------------------------------------------------ main arm
 def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if a.mode == "train":
+        return run_train(a)
 
     import torch.distributed as dist
     from sigma_b200 import dist_util

@@ -51,7 +51,11 @@ uint64_t sigma_launch_count(void);
  * strides given below; A (dim, dstate) any strides; B, C (batch, ngroups, dstate, seqlen) unit
  * stride along seqlen.  `x` (nullable) receives the chunk-end states
  * (batch, dim, ceil(seqlen/2048), 2·dstate) fp32, interleaved (prod a, h), contiguous
- * (selective_scan.cpp:228, fwd_kernel.cuh:181-184).  D and delta_bias are nullable.
+ * (selective_scan.cpp:228, fwd_kernel.cuh:181-184; the first component is the running product since the START of the
+ * sequence, as the reference's prefix callback keeps it).  D and delta_bias are nullable.  fp16 / bf16 are read and
+ * written natively.  Calls whose rows are 16-byte aligned, whose channel groups are multiples of 32 and d_state in
+ * {4, 8, 16} (every Sigma call) run the TMA-staged kernel (csrc/scan_op_tma.cu); anything else the generic one.
+ * `workspace` only holds the L-segment carries (sigma_scan_fwd_workspace_bytes); without it the scan runs unsplit.
  * ------------------------------------------------------------------------------------------ */
 typedef struct sigma_scan_strides {
   int64_t u_batch, u_dim;
@@ -76,7 +80,8 @@ int sigma_scan_fwd(const void *u, const void *delta, const float *A, const void 
  * Replaces `selective_scan_cuda_core.bwd(u, delta, A, B, C, D, delta_bias, dout, x,
  * delta_softplus, nrows) -> [du, ddelta, dA, dB, dC, dD, ddelta_bias]`
  * (selective_scan.cpp:251-362, selective_scan_bwd_kernel.cuh:68-274).
- * All tensors contiguous (d_state <= 16).  `workspace` holds the per-tile forward states of the recompute sweep;
+ * All tensors contiguous (d_state <= 16), fp16 / bf16 natively.  `workspace` holds the forward states of the recompute sweep
+ * (one every 16 positions) and the L-segment carries of both directions;
  * the reference's `x` is not needed.  du, ddelta: (batch, dim, seqlen) in `dtype`; dA (dim, dstate),
  * dD, ddelta_bias (dim) fp32 — OVERWRITTEN (not accumulated); dB, dC (batch, ngroups, dstate,
  * seqlen) fp32, overwritten.  dD / ddelta_bias may be NULL when D / delta_bias are NULL.
@@ -195,10 +200,48 @@ int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *
  * counts[0] (labeled) += 1, counts[1] (correct) += (pred == label).  hist (classes²) and counts (2) are uint64
  * ACCUMULATORS in device memory (zero them once per evaluation); labels (batch, H, W) are uint8 / int32 / int64
  * (label_bytes = 1 / 4 / 8), anything outside [0, classes) — e.g. 255 — is ignored; pred (batch·H·W uint8) may be NULL.
+ * num_classes <= 238 (the per-CTA histogram lives in shared memory).
  * ------------------------------------------------------------------------------------------ */
 int sigma_argmax_hist_fwd(const float *logits, const void *labels, int label_bytes, uint64_t *hist,
                           uint64_t *counts, uint8_t *pred, int batch, int num_classes, int64_t HW,
                           void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * the callers either side of the hot path, on the device.
+ *
+ * sigma_image_pre_fwd — the pre-processing of ONE image into one (3, OH, OW) float32 network input (and optionally its
+ * (OH, OW) int64 label map): replaces, in one kernel, TrainPre.__call__ (dataloader/dataloader.py:26-50: random_mirror,
+ * random_scale = cv2.resize INTER_LINEAR / INTER_NEAREST, normalize, random_crop_pad_to_shape) and the evaluator's
+ * process_image_rgbX (engine/evaluator.py:523-558: normalize + pad_image_to_shape) incl. the multi-scale cv2.resize of
+ * sliding_eval_rgbX (:439-444) and the horizontal flip of the padded input (:512-515).  The random choices are made by the
+ * caller and passed in.  src (H0, W0, 3) uint8 HWC; labels (H0, W0) uint8 or NULL.
+ *   scaled image = cv2.resize(src [flipped horizontally first if mirror_src], (SW, SH), INTER_LINEAR), 8-bit fixed-point
+ *                  arithmetic of OpenCV's generic path (scale_y / scale_x = source pixels per scaled pixel: 1/fy, 1/fx, or
+ *                  H0/SH, W0/SW); SH == H0 and SW == W0: no resize
+ *   out(c, oy, ox) = ((scaled(oy + off_y, ox + off_x, c) / 255) - mean[c]) / std[c]  (double, utils/transforms.py:182-187),
+ *                    0 outside the scaled image — or outside the rectangle clip4_host = {y0, x0, h, w} of it when given (a sliding
+ *                    window, evaluator.py:478-482) —; label_out = label_pad there (255 in TrainPre); mirror_out flips the OUTPUT.
+ * ------------------------------------------------------------------------------------------ */
+int sigma_image_pre_fwd(const uint8_t *src, const uint8_t *labels, float *out, int64_t *labels_out, int H0, int W0, int SH, int SW,
+                        double scale_y, double scale_x, int OH, int OW, int off_y, int off_x, int mirror_src, int mirror_out,
+                        int label_pad, const int *clip4_host, const double *mean3_host, const double *std3_host, void *stream);
+
+/* evaluator.py:505-520 and 481-488: acc[c, ay + y, ax + x] += exp(logits[c, m_top + y, m_left + x] (+ logits_flip[c, m_top + y,
+ * TW - 1 - (m_left + x)])) for y < vh, x < vw.  logits (ncls, TH, TW) = one image of the model's NCHW output; logits_flip
+ * (nullable) = the output for the horizontally flipped input; acc (ncls, AH, AW) float32 = the scale's score map.         */
+int sigma_eval_exp_accumulate_fwd(const float *logits, const float *logits_flip, float *acc, int ncls, int TH, int TW, int m_top,
+                                  int m_left, int vh, int vw, int AH, int AW, int ay, int ax, void *stream);
+
+/* evaluator.py:497-499 and 447-448: out (H0, W0, ncls) float64 += cv2.resize(acc[:, m_top : m_top + SH, m_left : m_left + SW]
+ * as HWC float32, (W0, H0), INTER_LINEAR) (cv2's float path; identity when SH == H0 and SW == W0).                        */
+int sigma_eval_resize_add_fwd(const float *acc, int ncls, int AH, int AW, int m_top, int m_left, int SH, int SW, double *out,
+                              int H0, int W0, void *stream);
+
+/* evaluator.py:451 + eval.py:28 + utils/metric.py:8-15: pred = argmax over classes of score (HW, ncls) float64 (first maximum,
+ * numpy.argmax); labels (HW) uint8 nullable: hist[label·ncls + pred] += 1, counts[0] (labeled) += 1, counts[1] (correct)
+ * += (pred == label) for label < ncls.  hist / counts are uint64 accumulators.                                            */
+int sigma_eval_argmax_hist_fwd(const double *score, const uint8_t *labels, uint8_t *pred, uint64_t *hist, uint64_t *counts,
+                               int num_classes, int64_t HW, void *stream);
 
 #ifdef __cplusplus
 }

@@ -2,7 +2,7 @@
 library is missing or a call fails, a RuntimeError carrying sigma_last_error() is raised."""
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsigma_b200.so")
@@ -43,6 +43,10 @@ SIGNATURES = {
     "sigma_upsample2x_norm_head_fwd": (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 4 + [c_float, c_void_p]),
     "sigma_pool_avgmax_partial_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, c_int, c_void_p]),
     "sigma_scale_add_fwd": (c_int, [c_void_p] * 5 + [c_int64, c_int64, c_int, c_void_p]),
+    "sigma_image_pre_fwd": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_double, c_double] + [c_int] * 7 + [c_void_p] * 4),
+    "sigma_eval_exp_accumulate_fwd": (c_int, [c_void_p] * 3 + [c_int] * 11 + [c_void_p]),
+    "sigma_eval_resize_add_fwd": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p]),
+    "sigma_eval_argmax_hist_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_void_p]),
     "sigma_linear_tf32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
 }
 

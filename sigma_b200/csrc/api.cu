@@ -167,6 +167,19 @@ int scale_add_launch(const float *a, const float *sa, const float *b, const floa
                      long long rows_per_batch, int C, cudaStream_t stream);
 int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *bias, const float *residual, long long ldr,
                      const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream);
+struct ImagePreParams {
+  const unsigned char *src; float *dst; const unsigned char *lsrc; long long *ldst;
+  int H0, W0, SH, SW, OH, OW, off_y, off_x, mirror_src, mirror_out, label_pad;
+  int clip_y0, clip_x0, clip_y1, clip_x1;
+  double scale_y, scale_x, mean[3], stdv[3];
+};
+int image_pre_launch(const ImagePreParams &p, cudaStream_t stream);
+int eval_exp_accumulate_launch(const float *logits, const float *logits_flip, float *acc, int ncls, int TH, int TW, int m_top, int m_left,
+                               int vh, int vw, int AH, int AW, int ay, int ax, cudaStream_t stream);
+int eval_resize_add_launch(const float *acc, int ncls, int AH, int AW, int m_top, int m_left, int SH, int SW, double *out, int H0, int W0,
+                           cudaStream_t stream);
+int eval_argmax_hist_launch(const double *score, const unsigned char *labels, unsigned char *pred, unsigned long long *hist,
+                            unsigned long long *counts, int ncls, long long HW, cudaStream_t stream);
 static bool al16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 }  // namespace sigma
 
@@ -298,7 +311,7 @@ int sigma_upsample2x_norm_head_fwd(const float *x, const float *w, const float *
 int sigma_argmax_hist_fwd(const float *logits, const void *labels, int label_bytes, uint64_t *hist, uint64_t *counts,
                           uint8_t *pred, int batch, int num_classes, int64_t HW, void *stream) {
   SIGMA_CHECK_ARG(logits && labels && hist && counts, "sigma_argmax_hist_fwd: null pointer");
-  SIGMA_CHECK_ARG(batch > 0 && HW > 0 && num_classes > 0 && num_classes <= 255, "sigma_argmax_hist_fwd: bad sizes (1 <= classes <= 255)");
+  SIGMA_CHECK_ARG(batch > 0 && HW > 0 && num_classes > 0 && num_classes <= 238, "sigma_argmax_hist_fwd: bad sizes (1 <= classes <= 238: the per-CTA histogram lives in shared memory)");
   return argmax_hist_launch(logits, labels, label_bytes, (unsigned long long *)hist, (unsigned long long *)counts, pred, batch,
                             num_classes, HW, (cudaStream_t)stream);
 }
@@ -373,12 +386,63 @@ int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *
                       const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream) {
   SIGMA_CHECK_ARG(A && W && C, "sigma_linear_tf32: null pointer");
   SIGMA_CHECK_ARG(M >= 0 && M < (1LL << 31) && N > 0 && K > 0, "sigma_linear_tf32: bad sizes M=%lld N=%d K=%d", (long long)M, N, K);
-  SIGMA_CHECK_ARG(K % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && (residual == nullptr || ldr % 4 == 0) && lda >= K && ldc >= N,
-                  "sigma_linear_tf32: K, lda, ldc, ldr must be multiples of 4 floats (16-byte TMA / vector alignment)");
+  SIGMA_CHECK_ARG(K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && (residual == nullptr || ldr % 4 == 0) && lda >= K && ldc >= N,
+                  "sigma_linear_tf32: K, N, lda, ldc, ldr must be multiples of 4 floats (16-byte TMA boxes; the epilogue reads bias / "
+                  "rscale / residual as float4)");
   SIGMA_CHECK_ARG(al16(A) && al16(W) && al16(C) && al16(bias) && al16(residual) && al16(rscale),
                   "sigma_linear_tf32: pointers must be 16-byte aligned");
   SIGMA_CHECK_ARG(rscale == nullptr || residual != nullptr, "sigma_linear_tf32: rscale without residual");
   return gemm_tf32_launch(A, lda, W, bias, residual, ldr, rscale, C, ldc, M, N, K, (cudaStream_t)stream);
+}
+
+int sigma_image_pre_fwd(const uint8_t *src, const uint8_t *labels, float *out, int64_t *labels_out, int H0, int W0, int SH, int SW,
+                        double scale_y, double scale_x, int OH, int OW, int off_y, int off_x, int mirror_src, int mirror_out,
+                        int label_pad, const int *clip4_host, const double *mean3, const double *std3, void *stream) {
+  SIGMA_CHECK_ARG(src && out && mean3 && std3, "sigma_image_pre_fwd: null pointer");
+  SIGMA_CHECK_ARG((labels == nullptr) == (labels_out == nullptr), "sigma_image_pre_fwd: labels and labels_out go together");
+  SIGMA_CHECK_ARG(H0 > 0 && W0 > 0 && SH > 0 && SW > 0 && OH > 0 && OW > 0 && scale_y > 0 && scale_x > 0, "sigma_image_pre_fwd: bad sizes");
+  ImagePreParams p;
+  p.src = src; p.dst = out; p.lsrc = labels; p.ldst = (long long *)labels_out;
+  p.H0 = H0; p.W0 = W0; p.SH = SH; p.SW = SW; p.OH = OH; p.OW = OW; p.off_y = off_y; p.off_x = off_x;
+  p.mirror_src = mirror_src; p.mirror_out = mirror_out; p.label_pad = label_pad; p.scale_y = scale_y; p.scale_x = scale_x;
+  p.clip_y0 = 0; p.clip_x0 = 0; p.clip_y1 = SH; p.clip_x1 = SW;
+  if (clip4_host) {
+    p.clip_y0 = std::max(0, clip4_host[0]); p.clip_x0 = std::max(0, clip4_host[1]);
+    p.clip_y1 = std::min(SH, clip4_host[0] + clip4_host[2]); p.clip_x1 = std::min(SW, clip4_host[1] + clip4_host[3]);
+  }
+  for (int c = 0; c < 3; ++c) {
+    SIGMA_CHECK_ARG(std3[c] != 0.0, "sigma_image_pre_fwd: std[%d] == 0", c);
+    p.mean[c] = mean3[c]; p.stdv[c] = std3[c];
+  }
+  return image_pre_launch(p, (cudaStream_t)stream);
+}
+
+int sigma_eval_exp_accumulate_fwd(const float *logits, const float *logits_flip, float *acc, int ncls, int TH, int TW, int m_top,
+                                  int m_left, int vh, int vw, int AH, int AW, int ay, int ax, void *stream) {
+  SIGMA_CHECK_ARG(logits && acc, "sigma_eval_exp_accumulate_fwd: null pointer");
+  SIGMA_CHECK_ARG(ncls > 0 && m_top >= 0 && m_left >= 0 && vh >= 0 && vw >= 0 && m_top + vh <= TH && m_left + vw <= TW && ay >= 0 &&
+                      ax >= 0 && ay + vh <= AH && ax + vw <= AW,
+                  "sigma_eval_exp_accumulate_fwd: window (%d+%d, %d+%d) of a %dx%d tile into (%d, %d) of %dx%d", m_top, vh, m_left, vw,
+                  TH, TW, ay, ax, AH, AW);
+  return eval_exp_accumulate_launch(logits, logits_flip, acc, ncls, TH, TW, m_top, m_left, vh, vw, AH, AW, ay, ax, (cudaStream_t)stream);
+}
+
+int sigma_eval_resize_add_fwd(const float *acc, int ncls, int AH, int AW, int m_top, int m_left, int SH, int SW, double *out, int H0,
+                              int W0, void *stream) {
+  SIGMA_CHECK_ARG(acc && out, "sigma_eval_resize_add_fwd: null pointer");
+  SIGMA_CHECK_ARG(ncls > 0 && SH > 0 && SW > 0 && H0 > 0 && W0 > 0 && m_top >= 0 && m_left >= 0 && m_top + SH <= AH && m_left + SW <= AW,
+                  "sigma_eval_resize_add_fwd: bad sizes");
+  return eval_resize_add_launch(acc, ncls, AH, AW, m_top, m_left, SH, SW, out, H0, W0, (cudaStream_t)stream);
+}
+
+int sigma_eval_argmax_hist_fwd(const double *score, const uint8_t *labels, uint8_t *pred, uint64_t *hist, uint64_t *counts,
+                               int num_classes, int64_t HW, void *stream) {
+  SIGMA_CHECK_ARG(score && pred, "sigma_eval_argmax_hist_fwd: null pointer");
+  SIGMA_CHECK_ARG(labels == nullptr || (hist && counts), "sigma_eval_argmax_hist_fwd: labels need hist and counts");
+  SIGMA_CHECK_ARG(num_classes >= 1 && num_classes <= 255 && HW >= 0, "sigma_eval_argmax_hist_fwd: bad sizes");
+  if (HW == 0) return SIGMA_OK;
+  return eval_argmax_hist_launch(score, labels, pred, (unsigned long long *)hist, (unsigned long long *)counts, num_classes, HW,
+                                 (cudaStream_t)stream);
 }
 
 #pragma GCC visibility pop

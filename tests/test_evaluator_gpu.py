@@ -1,0 +1,92 @@
+"""GPU: the callers either side of the hot path on the device against the oracle restatement
+of engine/evaluator.py:433-558 and dataloader/dataloader.py:8-50 (oracle/evaluator_ref.py, which uses cv2 / numpy exactly
+where the reference does).  The SAME model (our fused forward) is the `val_func` of both sides, so what is compared is the
+evaluator / pre-processing logic: resize, normalize, pad, flip, exp, window accumulation, resize back, argmax, hist.
+Integer / index outputs are bit-exact; where cv2's float resize or its IPP-accelerated 8-bit up-scaling is involved the
+bar is stated in the test."""
+import contextlib
+import io
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import procedural as P
+from helpers import SEED, cfg_tiny
+from oracle import evaluator_ref as ER, sigma_ref
+
+pytestmark = pytest.mark.gpu
+MEAN, STD = np.array([0.485, 0.456, 0.406]), np.array([0.229, 0.224, 0.225])
+NCLS = 9
+
+
+def _images(h, w, seed):
+    rng = np.random.default_rng(seed)
+    # smooth-ish content so that resizing matters: low-frequency pattern + noise
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = (127 + 90 * np.sin(yy / 17.0)[..., None] * np.cos(xx / 23.0)[..., None] * np.array([1.0, 0.7, -0.8])).clip(0, 255)
+    rgb = (base + rng.integers(-30, 30, (h, w, 3))).clip(0, 255).astype(np.uint8)
+    mx = (255 - base + rng.integers(-40, 40, (h, w, 3))).clip(0, 255).astype(np.uint8)
+    gt = rng.integers(0, NCLS + 1, (h, w)).astype(np.uint8)
+    gt[gt == NCLS] = 255
+    return rgb, mx, gt
+
+
+@pytest.fixture(scope="module")
+def model():
+    from sigma_b200 import modules as M
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = M.EncoderDecoder(cfg_tiny(96, 128, num_classes=NCLS), criterion=None)
+    P.fill_state_dict(m, SEED + 21)
+    return m.cuda().eval()
+
+
+def _val_func(model):
+    def f(a, b):
+        with torch.no_grad():
+            return model(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+    return f
+
+
+@pytest.mark.parametrize("scales,flip,hw,crop,min_agree", [
+    ((1,), False, (96, 128), (96, 128), 1.0),            # the reference's default eval config: whole image, one scale
+    ((1,), True, (96, 128), (96, 128), 1.0),             # + flip
+    ((1,), False, (80, 100), (96, 128), 1.0),            # image smaller than the crop: centred padding, margins cropped
+    ((0.75, 1), True, (96, 128), (96, 128), 0.999),      # down-scaling: cv2's 8-bit fixed-point resize is reproduced exactly; float resize back
+    ((1, 1.5), False, (96, 128), (96, 96), 0.995),       # 1.5x -> 144x192 > crop: sliding windows (square crop); IPP up-scaling differs by 1 LSB on ~0.1 % of pixels
+])
+def test_device_evaluator_matches_reference_logic(model, scales, flip, hw, crop, min_agree):
+    from sigma_b200.evaluator import DeviceEvaluator
+    rgb, mx, gt = _images(hw[0], hw[1], 5)
+    ref = ER.sliding_eval_rgbX(_val_func(model), rgb, mx, crop, 2 / 3, list(scales), flip, NCLS, MEAN, STD)
+    ev = DeviceEvaluator(model, NCLS, MEAN, STD, crop, 2 / 3, multi_scales=scales, is_flip=flip)
+    pred = ev.sliding_eval_rgbX(rgb, mx, gt).cpu().numpy()
+    agree = float((pred == ref).mean())
+    assert agree >= min_agree, f"labels equal to the reference evaluator's: {agree:.5f} (need {min_agree})"
+    hist, labeled, correct = ev.metric.result()
+    h2, l2, c2 = sigma_ref.hist_info(NCLS, pred, gt)
+    assert (hist == h2).all() and labeled == l2 and correct == c2, "device confusion matrix != utils/metric.py on the device prediction"
+
+
+@pytest.mark.parametrize("scale,mirror,hw,crop", [(None, False, (96, 128), (96, 128)), (0.75, True, (120, 160), (96, 128)),
+                                                 (0.5, False, (120, 160), (96, 128)), (1.25, True, (96, 128), (96, 128))])
+def test_device_train_pre_matches_reference(scale, mirror, hw, crop):
+    """TrainPre on the device vs the cv2 / numpy restatement, same random draws."""
+    from sigma_b200.evaluator import DeviceTrainPre
+    rgb, mx, gt = _images(hw[0], hw[1], 9)
+    pre = DeviceTrainPre(MEAN, STD, crop[0], crop[1], train_scale_array=[scale] if scale else None)
+    rng = random.Random(3)
+    _, _, pos = pre.draw(hw[0], hw[1], rng)
+    r_rgb, r_gt, r_x = ER.train_pre(rgb, gt, mx, mirror, scale, pos, crop, MEAN, STD)
+    o_rgb = torch.empty((3, crop[0], crop[1]), device="cuda")
+    o_x = torch.empty_like(o_rgb)
+    o_gt = torch.empty((crop[0], crop[1]), dtype=torch.int64, device="cuda")
+    pre(torch.from_numpy(rgb).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(mx).cuda(), o_rgb, o_gt, o_x, mirror, scale, pos)
+    assert (o_gt.cpu().numpy() == r_gt.astype(np.int64)).all(), "labels (nearest resize, crop, 255 padding)"
+    for got, ref, nm in ((o_rgb, r_rgb, "rgb"), (o_x, r_x, "modal_x")):
+        d = np.abs(got.cpu().numpy() - ref.astype(np.float32))
+        if scale is None or scale < 1:
+            assert d.max() == 0.0, f"{nm}: not bit-exact (max {d.max():.3e})"
+        else:   # up-scaling: OpenCV's IPP path differs from its own generic path by one 8-bit step on a few pixels
+            assert d.max() <= 1.01 / 255 / STD.min() and float((d > 0).mean()) < 5e-3, f"{nm}: {d.max():.3e}, {float((d > 0).mean()):.4f} of pixels differ"
