@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cublas-gemm", action="store_true", help="A/B: dense projections through cuBLAS instead of our tcgen05 GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-by-batch", action="store_true", help="skip the B = 1..16 sweep appended to the line at N = 1")
     ap.add_argument("--cpu-sample-images", type=int, default=2)
     a = ap.parse_args()
     if a.batch is None:
@@ -79,18 +80,25 @@ def cpu_threads():
     return n
 
 
+def cpu_state_dict(a):
+    """Random-init weights for the CPU arm WITHOUT importing the product: shapes from oracle/state_shapes.json (the reference's
+    checkpoint contract), values from tests/procedural.py's role-aware deterministic fill (the goldens' generator)."""
+    import procedural as P
+    shapes = json.load(open(os.path.join(ROOT, "oracle", "state_shapes.json")))[a.model]
+    sd = {}
+    for k, shp in shapes.items():
+        if k == "decode_head.output.weight":
+            shp = [a.num_classes] + list(shp[1:])
+        sd[k] = P.fill_param(0, k, shp) if shp else torch.zeros(())
+    return sd
+
+
 def cpu_reference_images_per_s(a, n_images, quiet=True):
     """The oracle port of the reference's CPU path (oracle/sigma_ref.py + oracle/selective_scan_ref.c:
     torch-CPU dense ops, multi-threaded C selective scan), one image at a time as engine/evaluator.py does."""
-    import contextlib
-    import io
     from oracle import scan_oracle, sigma_ref
-    from sigma_b200 import modules as M
     scan_oracle.build()
-    torch.manual_seed(0)
-    with contextlib.redirect_stdout(io.StringIO()):
-        model = M.EncoderDecoder(cfg_of(a), criterion=None)
-    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    sd = cpu_state_dict(a)
     g = torch.Generator().manual_seed(1234)
     rgb = torch.randn(1, 3, a.height, a.width, generator=g)
     mx = torch.randn(1, 3, a.height, a.width, generator=g)
@@ -118,7 +126,8 @@ def run_reference(a):
         "impl": "reference", "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(ips, 5), "unit": "images/s",
         "n_gpus": a.gpus, "steps": n, "warmup": min(a.warmup, 1), "ms_per_step": round(1e3 * dt / n, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample": "1 image per step (bounded sample of the batch)"},
+        "config": {"workload": workload_name(a), "sample": "1 image per step (bounded sample of the batch)",
+                   "cpu_ranks": 1, "note": "under torchrun only rank 0 runs the CPU arm: the ratio at N > 1 is against ONE host process"},
         "cpu_baseline": {"value": round(ips, 5), "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{n} x 1 image {a.height}x{a.width}, oracle port (C selective scan with OpenMP + torch CPU)"},
         "e2e": {"value": round(ips, 5), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -176,6 +185,94 @@ class ClockSampler:
             pass
         return out
 
+
+
+# ------------------------------------------------------------------ GPU baseline: the reference's own CUDA extension
+REF_CALLS = {  # per image: name, KD, L, N, K, calls for tiny / small (base uses its own dims below)
+    "enc0": (768, 19200, 16, 4, (4, 4)), "enc1": (1536, 4800, 16, 4, (4, 4)), "enc2": (3072, 1200, 16, 4, (18, 54)),
+    "enc3": (6144, 300, 16, 4, (4, 4)), "cromb0": (192, 19200, 4, 1, (2, 2)), "cromb1": (384, 4800, 4, 1, (2, 2)),
+    "cromb2": (768, 1200, 4, 1, (2, 2)), "cromb3": (1536, 300, 4, 1, (2, 2)), "conmb0": (384, 38400, 4, 2, (1, 1)),
+    "conmb1": (768, 9600, 4, 2, (1, 1)), "conmb2": (1536, 2400, 4, 2, (1, 1)), "conmb3": (3072, 600, 4, 2, (1, 1)),
+    "dec2": (3072, 1200, 4, 4, (4, 4)), "dec1": (1536, 4800, 4, 4, (4, 4)), "dec0": (768, 19200, 4, 4, (4, 4)),
+}
+
+
+def measure_gpu_baseline(a, dev, batch=8):
+    """The reference's selective_scan_cuda_core rebuilt for sm_100a (baseline/_ref, recipe baseline/build_ref_ext.py) on the
+    scan calls of one forward at 480x640 (synthetic tensors of the calls' shapes, `batch` images, best of nrows 1 / 4 as
+    vmamba.py:183-191 would pick): aggregate algorithmic GB/s and ms per image — the GPU baseline the fused scan replaces."""
+    so = os.path.join(ROOT, "baseline", "_ref", "selective_scan_cuda_core.so")
+    if not os.path.exists(so) or a.model not in ("sigma_tiny", "sigma_small") or (a.height, a.width) != (480, 640):
+        return None
+    try:
+        sys.path.insert(0, os.path.dirname(so))
+        import selective_scan_cuda_core as ref
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    col = 0 if a.model == "sigma_tiny" else 1
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev).manual_seed(5)
+    tot_ms = tot_b = 0.0
+    for name, (KD, L, N, K, calls) in REF_CALLS.items():
+        u = torch.randn(batch, KD, L, device=dev, generator=g)
+        dl = torch.randn(batch, KD, L, device=dev, generator=g) * 0.7
+        A = -(torch.rand(KD, N, device=dev, generator=g) * N + 0.3)
+        Bm = torch.randn(batch, K, N, L, device=dev, generator=g)
+        Cm = torch.randn(batch, K, N, L, device=dev, generator=g)
+        D = torch.randn(KD, device=dev, generator=g)
+        bias = torch.rand(KD, device=dev, generator=g) * 4 - 6
+        best = None
+        for nrows in ((1, 4) if K > 1 and (KD // K) % 4 == 0 else (1,)):
+            ref.fwd(u, dl, A, Bm, Cm, D, bias, True, nrows)
+            ts = []
+            for _ in range(3):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ref.fwd(u, dl, A, Bm, Cm, D, bias, True, nrows)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            t = sorted(ts)[1]
+            best = t if best is None else min(best, t)
+        tot_ms += best * calls[col]
+        tot_b += (4 * (3 * batch * KD * L + 2 * batch * K * N * L) + 4 * (KD * N + 2 * KD)) * calls[col]
+        del u, dl, Bm, Cm
+    return {"kind": "reference selective_scan_cuda_core rebuilt for sm_100a (--use_fast_math), its own (B,KD,L) layout, nrows best of 1/4",
+            "batch": batch, "scan_ms_per_image": round(tot_ms / batch, 3), "GBps": round(tot_b / tot_ms / 1e6, 1),
+            "calls_per_image": sum(c[4][col] for c in REF_CALLS.values()),
+            "note": "kernel time of the scan calls only: the reference additionally materialises CrossScan / delta / CrossMerge around them"}
+
+
+def measure_by_batch(model, a, dev, batches=(1, 2, 4, 8, 16)):
+    """images/s by per-GPU batch (CUDA-graph replay, resident inputs, L2 flush between steps)."""
+    from sigma_b200.pipeline import InferencePipeline
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {}
+    for b in batches:
+        try:
+            pipe = InferencePipeline(model, b, a.height, a.width, use_graph=True)
+            pipe.rgb.normal_()
+            pipe.x.normal_()
+            for _ in range(3):
+                pipe.graph.replay()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                pipe.graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ms = sorted(ts)[len(ts) // 2]
+            out[str(b)] = {"ms_per_step": round(ms, 3), "images_per_s": round(b / ms * 1e3, 2)}
+            del pipe
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[str(b)] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 # ------------------------------------------------------------------ roofline instrumentation
 def scan_algo_bytes(kind, batch, H, W, D, N):
@@ -531,15 +628,21 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = tot_b / (tot_ms * 1e-3) / 1e9
-    traffic = None
+    # DRAM bytes actually moved by the scan launches of one step: from the ncu capture of THIS command at this batch
+    # (profiles/r02_scan_traffic.json, written by scripts/ncu_scan_traffic.py: dram__bytes_read.sum + dram__bytes_write.sum
+    # summed over the scan launches of one step, divided by the launch count); null when no capture matches the configuration
+    traffic, traffic_src = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "scan_traffic.json"))).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_scan_traffic.json")))
+        if tj.get("batch") == B and tj.get("model") == a.model and [tj.get("height"), tj.get("width")] == [a.height, a.width]:
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": "ss2d_scan_kernel (fused 4/2/1-direction selective scan)",
                 "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                "traffic": traffic, "calls_per_step": ncalls // passes,
+                "traffic": traffic, "traffic_source": traffic_src, "calls_per_step": ncalls // passes,
+                "algorithmic_bytes_per_launch": (tot_b // passes) // max(1, ncalls // passes),
                 "algorithmic_bytes_per_step": tot_b // passes, "scan_ms_per_step": round(tot_ms / passes, 3),
                 "by_dstate": {str(n): {"GBps": round(v[0] / (v[1] * 1e-3) / 1e9, 1), "ms_per_step": round(v[1] / passes, 3),
                                        "calls": v[2] // passes} for n, v in sorted(by_n.items())}}
@@ -552,6 +655,8 @@ def main():
                "sample": f"{a.cpu_sample_images} images {a.height}x{a.width} one at a time ({dt:.1f} s): oracle port of the "
                          "reference CPU path (C selective scan with OpenMP + torch CPU dense ops)"}
 
+    gpu_base = measure_gpu_baseline(a, dev) if world == 1 else None
+    by_batch = measure_by_batch(model, a, dev) if (world == 1 and not a.no_by_batch) else None
     n_img = B * world * a.steps
     in_bytes = 2 * B * 3 * a.height * a.width * 4
     out_bytes = static_out.numel() * static_out.element_size()
@@ -564,7 +669,7 @@ def main():
                    "dense_math": "tf32 tensor cores (hand-written tcgen05 GEMM), fp32 accumulate" if fused.USE_TCGEN05_GEMM else "tf32 cuBLAS", "cuda_graph": graph is not None,
                    "l2": "256 MiB flush between timed steps",
                    "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "by_batch": by_batch,
         "e2e": {"value": round(n_img / (e2e_ms * 1e-3), 3), "unit": "images/s", "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": out_bytes, "mode": e2e_mode},
         "gpu_launches": int(launches_per_step) * a.steps,

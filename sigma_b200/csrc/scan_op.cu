@@ -336,7 +336,6 @@ static void plan_split(ScanOpParams &p, int lpc, bool have_ws, int force_split) 
   if (force_split > 0) nsplit = force_split;
   if (!have_ws) nsplit = 1;
   int tps = (p.ntiles + nsplit - 1) / nsplit;
-  if (p.x != nullptr && nsplit > 1) tps = ((tps + 63) / 64) * 64;  // segments end on 2048-chunk boundaries
   tps = std::max(tps, 1);
   nsplit = (p.ntiles + tps - 1) / tps;
   p.tiles_per_split = tps;

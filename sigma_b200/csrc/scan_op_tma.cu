@@ -360,16 +360,17 @@ int scan_op_fwd_tma(const void *u, const void *delta, const float *A, const void
   p.nchunks = (L + 2047) / 2048;
   p.nhs = (L + OPT_HS_POS - 1) / OPT_HS_POS;
 
-  // L-segments only when the unsplit grid leaves SM sub-partitions without a warp (as the fused kernel: a second pass
-  // over the data repeats every exponential)
+  // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY) when the unsplit grid cannot fill the 148 x 4 SM sub-partitions: a
+  // second pass repeats the exponentials, so the target is ~2 warps per sub-partition for d_state 16 and ~4 below
+  // (measured on B200, profiles/r02_op_split_sweep.txt).  Segments need not end on the 2048-position chunk boundaries of
+  // `x`: a segment that crosses one writes that chunk's state itself (true h, prefix product = carry-in x local).
   const long long warps = (long long)batch * (dim / 32), fullm = 148LL * 4;
+  const long long target = (N >= 16 ? 2 : 4) * fullm;
   int nsplit = 1;
-  if (warps < fullm) nsplit = (int)std::min<long long>(((N >= 16 ? fullm : 2 * fullm) + warps - 1) / warps, kOpMaxSplit);
+  if (warps < fullm) nsplit = (int)std::min<long long>((target + warps - 1) / warps, kOpMaxSplit);
   if (force_split > 0) nsplit = std::min(force_split, kOpMaxSplit);
   if (ws == nullptr || ws_bytes < scan_op_tma_workspace_bytes(batch, dim, N)) nsplit = 1;
-  int tps = (p.ntiles + nsplit - 1) / nsplit;
-  if (x != nullptr && nsplit > 1) { const int q = 2048 / LT; tps = ((tps + q - 1) / q) * q; }   // segments end on chunk boundaries
-  tps = std::max(tps, 1);
+  const int tps = std::max(1, (p.ntiles + nsplit - 1) / nsplit);
   p.tiles_per_split = tps;
   p.nsplit = std::max(1, (p.ntiles + tps - 1) / tps);
 

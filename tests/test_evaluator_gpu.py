@@ -51,7 +51,9 @@ def _val_func(model):
 
 @pytest.mark.parametrize("scales,flip,hw,crop,min_agree", [
     ((1,), False, (96, 128), (96, 128), 1.0),            # the reference's default eval config: whole image, one scale
-    ((1,), True, (96, 128), (96, 128), 1.0),             # + flip
+    ((1,), True, (96, 128), (96, 128), 0.9995),          # + flip: image and mirror image go through ONE batch-2 forward here, two batch-1
+                                                         #   forwards in the reference; the scan's L-segment count depends on the batch, so
+                                                         #   logits differ in the last bits and labels only at exact near-ties
     ((1,), False, (80, 100), (96, 128), 1.0),            # image smaller than the crop: centred padding, margins cropped
     ((0.75, 1), True, (96, 128), (96, 128), 0.999),      # down-scaling: cv2's 8-bit fixed-point resize is reproduced exactly; float resize back
     ((1, 1.5), False, (96, 128), (96, 96), 0.995),       # 1.5x -> 144x192 > crop: sliding windows (square crop); IPP up-scaling differs by 1 LSB on ~0.1 % of pixels

@@ -1,10 +1,10 @@
 """GPU: module-level and full-model parity against the goldens of the UNMODIFIED reference, for BOTH
 execution paths of sigma_b200.modules (fused inference kernels / composed training path).
 
-Tolerances: the composed path does the dense layers in plain fp32 (torch.backends TF32 off) so it
-is held to the op-level bar (1e-3 of the output scale); the fused path runs its projections on the
-tcgen05 tensor cores in TF32 (10-bit mantissa, fp32 accumulate) and is held to 1e-2 of the output
-scale plus label agreement and equal mIoU."""
+Tolerances: with torch.backends.cuda.matmul.allow_tf32 = False (torch's default, the reference's numerics) BOTH paths do
+the dense layers in full fp32 and are held to the op-level bar (1e-3 of the output scale); with the switch on, the fused
+path runs its projections on the tcgen05 tensor cores in TF32 (10-bit mantissa, fp32 accumulate) and is held to 1e-2 of
+the output scale plus label agreement and equal mIoU."""
 import numpy as np
 import pytest
 import torch
@@ -31,15 +31,18 @@ def _mk(mod):
 
 def _tol(path, ref):
     scale = float(np.abs(ref).max())
-    return (0.0, (1e-3 if path == "composed" else 1e-2) * scale)
+    return (0.0, (1e-2 if path == "fused_tf32" else 1e-3) * scale)
 
 
 def _ctx(path):
+    """composed: op-level kernels under torch ops; fused_fp32: fused kernels, full-precision projections (torch's default
+    switch, the reference's numerics); fused_tf32: fused kernels with the tcgen05 TF32 GEMM (what bench.py measures)."""
     from sigma_b200 import modules as M
+    torch.backends.cuda.matmul.allow_tf32 = path == "fused_tf32"
     return M.composed_path(path == "composed")
 
 
-PATHS = ["composed", "fused"]
+PATHS = ["composed", "fused_fp32", "fused_tf32"]
 
 
 @pytest.mark.parametrize("path", PATHS)
@@ -97,7 +100,7 @@ def test_sigma_tiny_logits_and_miou(path, tag, H, W, Bn):
     assert_close(logits, ref, *_tol(path, ref), f"{tag} ({path})")
     pred = logits.argmax(1).cpu().numpy()
     agree = float((pred == ref.argmax(1)).mean())
-    assert agree >= (0.999 if path == "composed" else 0.99), agree
+    assert agree >= (0.99 if path == "fused_tf32" else 0.999), agree
     gt = (P.rand(SEED, tag + "/gt", (Bn, H, W)) * 9).long().clamp(max=8).numpy()
     _, miou = sigma_ref.mean_iou(pred, gt, 9)
-    assert abs(miou - float(g["miou"])) < (5e-4 if path == "composed" else 3e-3)
+    assert abs(miou - float(g["miou"])) < (3e-3 if path == "fused_tf32" else 5e-4)
