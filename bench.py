@@ -43,6 +43,10 @@ def parse():
                     help="train: one step = forward + CE loss + backward + AdamW (train.py:164-172), torch DDP over NCCL when N > 1 "
                          "(BASELINE configs 3 / 4); default batch 2 per GPU")
     ap.add_argument("--amp", default="none", choices=["none", "bf16"], help="train mode: autocast dtype of the dense layers")
+    ap.add_argument("--scan-impl", default="sigma", choices=["sigma", "ref_ext"],
+                    help="train mode: ref_ext swaps ONLY the native op for the reference's own CUDA extension (baseline/_ref) under the "
+                         "same composition = the reference's training step on this box (the GPU baseline of the training arm)")
+    ap.add_argument("--train-graph", action="store_true", help="train mode, N = 1: capture the whole step (fwd + bwd + AdamW) in one CUDA graph")
     ap.add_argument("--model", default="sigma_tiny")
     ap.add_argument("--height", type=int, default=480)
     ap.add_argument("--width", type=int, default=640)
@@ -359,7 +363,13 @@ def run_train(a):
     torch.manual_seed(0)
     with contextlib.redirect_stdout(io.StringIO()):
         model = M.EncoderDecoder(cfg_of(a), criterion=torch.nn.CrossEntropyLoss(reduction="mean", ignore_index=255)).to(dev).train()
-    opt = train_util.make_optimizer(model)
+    if a.scan_impl == "ref_ext":
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import selective_scan_cuda_core as ref_ext
+        ops.selective_scan_cuda_core_fwd = lambda u, delta, A, Bm, Cm, D=None, bias=None, sp=False, nrows=1, **k: ref_ext.fwd(u, delta, A, Bm, Cm, D, bias, sp, nrows)
+        ops.selective_scan_cuda_core_bwd = lambda u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows=1, **k: ref_ext.bwd(u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows)
+    use_graph = a.train_graph and world == 1
+    opt = train_util.make_optimizer(model, capturable=use_graph)
     ddp = train_util.wrap_ddp(model, local)
     step_fn = train_util.TrainStep(ddp, opt, amp_dtype=torch.bfloat16 if a.amp == "bf16" else None)
     B = a.batch
@@ -382,6 +392,32 @@ def run_train(a):
     step_fn(rgb, mx, gt)
     torch.cuda.synchronize()
     launches_per_step = _lib.launch_count() - n0
+    eager_step = step_fn
+    graph_note = None
+    if use_graph:   # whole-step capture: at 2 images per GPU the eager step is bound by the host's launch rate, not by the GPU
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    eager_step(rgb, mx, gt)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cg):
+                static_loss = eager_step(rgb, mx, gt)
+            torch.cuda.synchronize()
+
+            def step_fn(r, m, t, sync=True):       # inputs are the static device tensors rgb / mx / gt (copied into by e2e)
+                if r is not rgb:
+                    rgb.copy_(r, non_blocking=True); mx.copy_(m, non_blocking=True); gt.copy_(t, non_blocking=True)
+                cg.replay()
+                return static_loss
+            graph_note = "whole step (fwd + bwd + AdamW) replayed from one CUDA graph"
+        except Exception as e:
+            graph_note = f"CUDA graph capture failed ({type(e).__name__}: {e}); eager"[:300]
+            step_fn = eager_step
+            torch.cuda.synchronize()
 
     def timed(fn):
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
@@ -431,7 +467,7 @@ def run_train(a):
 
     ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = fwd_rec, bwd_rec
     try:
-        step_fn(rgb, mx, gt, sync=False)
+        eager_step(rgb, mx, gt, sync=False)
         torch.cuda.synchronize()
     finally:
         ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = f0, b0
@@ -451,7 +487,8 @@ def run_train(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tot_b, tot_ms = agg[False][0] + agg[True][0], agg[False][1] + agg[True][1]
-    roofline = {"bound": "hbm", "kernel": "scan_op_tma_kernel + scan_op_bwd_tma_kernel (op-level selective scan, forward and backward)",
+    roofline = {"bound": "hbm", "kernel": "scan_op_tma_kernel + scan_op_bwd_tma_kernel (op-level selective scan, forward and backward)"
+                if a.scan_impl == "sigma" else "reference selective_scan_fwd_kernel / selective_scan_bwd_kernel (GPU baseline)",
                 "achieved": round(tot_b / (tot_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(tot_b / (tot_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
@@ -469,7 +506,9 @@ def run_train(a):
         "config": {"workload": f"{a.model} train step, synthetic RGB-X {a.height}x{a.width}, {a.num_classes} classes, CE loss, AdamW lr 6e-5 wd 0.01",
                    "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"DDP x{world} (NCCL all-reduce of {gb / 1e6:.0f} MB fp32 gradients per step)" if world > 1 else "single GPU",
-                   "path": "composed (torch autograd over sigma_scan_fwd / sigma_scan_bwd)", "l2": "256 MiB flush between timed steps",
+                   "path": "composed (torch autograd over sigma_scan_fwd / sigma_scan_bwd)" if a.scan_impl == "sigma" else
+                           "GPU BASELINE: the same composition over the reference's own selective_scan_cuda_core (rebuilt for sm_100a)",
+                   "scan_impl": a.scan_impl, "cuda_graph": graph_note, "l2": "256 MiB flush between timed steps",
                    "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
         "roofline": roofline, "cpu_baseline": None,
         "collective": {"grad_bytes": gb, "allreduce_ms": round(ar_s * 1e3, 3), "bus_GBps": None if ar_bw is None else round(ar_bw, 1),

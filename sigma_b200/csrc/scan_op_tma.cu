@@ -361,11 +361,11 @@ int scan_op_fwd_tma(const void *u, const void *delta, const float *A, const void
   p.nhs = (L + OPT_HS_POS - 1) / OPT_HS_POS;
 
   // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY) when the unsplit grid cannot fill the 148 x 4 SM sub-partitions: a
-  // second pass repeats the exponentials, so the target is ~2 warps per sub-partition for d_state 16 and ~4 below
-  // (measured on B200, profiles/r02_op_split_sweep.txt).  Segments need not end on the 2048-position chunk boundaries of
+  // second pass repeats the exponentials, so only below one warp per sub-partition; then ~4 warps per sub-partition win for
+  // every d_state (measured on B200, profiles/r02_op_split_sweep.txt: 192 warps of d_state 16 -> 16 segments 1.62 ms, 7: 1.96).  Segments need not end on the 2048-position chunk boundaries of
   // `x`: a segment that crosses one writes that chunk's state itself (true h, prefix product = carry-in x local).
   const long long warps = (long long)batch * (dim / 32), fullm = 148LL * 4;
-  const long long target = (N >= 16 ? 2 : 4) * fullm;
+  const long long target = 4 * fullm;
   int nsplit = 1;
   if (warps < fullm) nsplit = (int)std::min<long long>((target + warps - 1) / warps, kOpMaxSplit);
   if (force_split > 0) nsplit = std::min(force_split, kOpMaxSplit);

@@ -54,7 +54,10 @@ def logits_bar():
     return 1e-2 if precision() == "tf32" else 1e-3
 
 
-def linear(x2d, weight, bias=None, out=None, residual=None, rscale=None):
+_FP32_KINDS = set()   # experiment hook (scripts/tf32_error_budget.py): kinds of projections forced to full precision in tf32 mode
+
+
+def linear(x2d, weight, bias=None, out=None, residual=None, rscale=None, kind="dense"):
     """Dense projection out = x·W^T (+bias) (+residual·rscale).  precision() == "tf32": the hand-written tcgen05 TF32 GEMM
     (csrc/gemm_tf32.cu: TMA-fed, TMEM accumulators, fused epilogue); "fp32": cuBLAS SGEMM.  x2d (M, K) with unit column
     stride, row stride % 4 == 0; weight (N, K) contiguous."""
@@ -62,7 +65,7 @@ def linear(x2d, weight, bias=None, out=None, residual=None, rscale=None):
     N = weight.shape[0]
     if out is None:
         out = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
-    if precision() != "tf32" or not USE_TCGEN05_GEMM or K % 4 or x2d.stride(1) != 1 or x2d.stride(0) % 4 or N % 4:
+    if precision() != "tf32" or kind in _FP32_KINDS or not USE_TCGEN05_GEMM or K % 4 or x2d.stride(1) != 1 or x2d.stride(0) % 4 or N % 4:
         torch.mm(x2d, weight.t(), out=out)
         if bias is not None:
             out += bias
@@ -170,16 +173,16 @@ def ss2d(m, x, residual=None, rscale=None):
     B, H, W, C = x.shape
     D, N, R, L = m.d_inner, m.d_state, m.dt_rank, H * W
     c = _ssm_params(m)
-    xz = linear(x.view(B * L, C), m.in_proj.weight, m.in_proj.bias)                                    # (BL, 2D): [x | z]
+    xz = linear(x.view(B * L, C), m.in_proj.weight, m.in_proj.bias, kind="in_proj")                    # (BL, 2D): [x | z]
     xc = torch.empty((B, L, D), dtype=torch.float32, device=x.device)
     dwconv3x3_silu(xz, 2 * D, L * 2 * D, m.conv2d, xc, L * D, B, H, W, D)
-    xdbl = linear(xc.view(B * L, D), c["xproj"])                                                       # (BL, 4·Cp)
+    xdbl = linear(xc.view(B * L, D), c["xproj"], kind="x_proj")                                        # (BL, 4·Cp)
     y = ss2d_scan(_lib.DIRS_CROSS4, xc, xdbl, c["dtw"], c["dtb"], c["A"], c["Ds"], B, H, W, D, N, R, c["Cp"])
     yg = torch.empty((B * L, D), dtype=torch.float32, device=x.device)
     z = ctypes.c_void_p(xz.data_ptr() + 4 * D)
     merge_norm_gate(y, 4, B * L * D, 0, m.out_norm, z, 2 * D, None, yg, 0, D, B * L, B * L, D)
     res2d = residual.reshape(B * L, C) if residual is not None else None
-    return linear(yg, m.out_proj.weight, m.out_proj.bias, residual=res2d, rscale=rscale).view(B, H, W, C)
+    return linear(yg, m.out_proj.weight, m.out_proj.bias, residual=res2d, rscale=rscale, kind="out_proj").view(B, H, W, C)
 
 
 def vss_block(blk, x):
@@ -217,8 +220,8 @@ def cromb_ss2d(m, x_rgb, x_e, residual=False):
     xc = torch.empty((2 * B, L, D), dtype=torch.float32, device=dev)
     dwconv3x3_silu(xp, D, L * D, m.conv2d, xc, L * D, 2 * B, H, W, D)         # ONE conv for both modalities (:1629-1630)
     xdbl = torch.empty((2, B * L, c["Cp"]), dtype=torch.float32, device=dev)
-    linear(xc[:B].view(B * L, D), c["xproj1"], out=xdbl[0])
-    linear(xc[B:].view(B * L, D), c["xproj2"], out=xdbl[1])
+    linear(xc[:B].view(B * L, D), c["xproj1"], out=xdbl[0], kind="x_proj")
+    linear(xc[B:].view(B * L, D), c["xproj2"], out=xdbl[1], kind="x_proj")
     y = ss2d_scan(_lib.DIRS_CROSS, xc, xdbl, c["dtw"], c["dtb"], c["A"], c["Ds"], 2 * B, H, W, D, N, R, c["Cp"])  # (1,2B,L,D)
     yn = torch.empty((2, B * L, D), dtype=torch.float32, device=dev)
     merge_norm_gate(y, 1, 0, 0, cm.out_norm_1, None, 0, None, yn, 0, D, B * L, B * L, D)
@@ -242,7 +245,7 @@ def conmb_ss2d(m, x_rgb, x_e, residual=None):
     seq = torch.empty((B, 2 * L, D), dtype=torch.float32, device=dev)         # [rgb ‖ x] along L (vmamba.py:130)
     dwconv3x3_silu(tr, D, L * D, m.conv2d, seq, 2 * L * D, B, H, W, D)
     dwconv3x3_silu(te, D, L * D, m.conv2d_modalx, seq[:, L:], 2 * L * D, B, H, W, D)
-    xdbl = linear(seq.view(B * 2 * L, D), c["xproj"])                         # (B·2L, 2·Cp)
+    xdbl = linear(seq.view(B * 2 * L, D), c["xproj"], kind="x_proj")          # (B·2L, 2·Cp)
     y = ss2d_scan(_lib.DIRS_SEQ2, seq, xdbl, c["dtw"], c["dtb"], c["A"], c["Ds"], B, H, W, D, N, R, c["Cp"])  # (2,B,2L,D)
     # SE gates from the PRE-conv projections, applied crosswise (vmamba.py:1276-1281)
     g_r = m.fc1(tr.view(B, L, D).mean(dim=1))

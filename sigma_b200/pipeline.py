@@ -21,14 +21,22 @@ class InferencePipeline:
 
     `h_rgb`, `h_x`: pinned host tensors (batch, 3, H, W) fp32; `h_out`: pinned host tensor (batch, classes, H, W) that
     receives the logits of THAT batch.  `submit` returns immediately; results are valid after `drain()` (or after a
-    later `submit` that reuses the same staging slot has been drained — use `drain()` before reading `h_out`)."""
+    later `submit` that reuses the same staging slot has been drained — use `drain()` before reading `h_out`).
+
+    The model must be in eval mode.  The captured graph holds the device pointers of the model's parameters AND of the
+    packed SSM tensors the fused path derives from them (x_proj / dt / A = -exp(A_logs) / D copies, fused._cache): when
+    any parameter is modified in place afterwards (load_state_dict, an optimizer step) `submit` notices the changed
+    version counters and re-captures the graph, so stale packed copies are never replayed."""
 
     def __init__(self, model, batch, height, width, use_graph=True):
         self.model = model
         p = next(model.parameters())
         if p.device.type != "cuda":
             raise RuntimeError("sigma_b200.InferencePipeline needs the model on a CUDA device (there is no CPU path)")
+        if model.training:
+            raise RuntimeError("sigma_b200.InferencePipeline: call model.eval() first (the fused inference path has no DropPath / dropout)")
         self.dev = p.device
+        self.use_graph = use_graph
         self.shape = (batch, 3, height, width)
         self.rgb = torch.zeros(self.shape, device=self.dev)
         self.x = torch.zeros(self.shape, device=self.dev)
@@ -36,15 +44,8 @@ class InferencePipeline:
         self.copy_in = torch.cuda.Stream(self.dev)
         self.copy_out = torch.cuda.Stream(self.dev)
         self.graph = None
-        with torch.cuda.stream(self.compute), torch.no_grad():
-            for _ in range(2):                       # warm-up: allocator, kernel attributes, cuDNN algorithm choice
-                self.out = model(self.rgb, self.x)
-        self.compute.synchronize()
-        if use_graph:
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=self.compute), torch.no_grad():
-                self.out = model(self.rgb, self.x)
-            self.compute.synchronize()
+        self.out = None
+        self._capture()
         self.stage_in = [(torch.empty_like(self.rgb), torch.empty_like(self.x)) for _ in range(2)]
         self.stage_out = [torch.empty_like(self.out) for _ in range(2)]
         self.ev_in = [torch.cuda.Event() for _ in range(2)]        # H2D into stage_in[s] finished
@@ -53,11 +54,30 @@ class InferencePipeline:
         self.ev_out_free = [torch.cuda.Event() for _ in range(2)]  # D2H out of stage_out[s] finished
         self.n = 0
 
+    def _versions(self):
+        return sum(p._version for p in self.model.parameters())
+
+    def _capture(self):
+        with torch.cuda.stream(self.compute), torch.no_grad():
+            for _ in range(2):                       # warm-up: allocator, kernel attributes, cuDNN algorithm choice, packed-parameter cache
+                out = self.model(self.rgb, self.x)
+        self.compute.synchronize()
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.compute), torch.no_grad():
+                out = self.model(self.rgb, self.x)
+            self.compute.synchronize()
+        self.out = out                               # the graph's static output tensor
+        self._ver = self._versions()
+
     @property
     def out_shape(self):
         return tuple(self.out.shape)
 
     def submit(self, h_rgb, h_x, h_out):
+        if self._versions() != self._ver:            # weights changed in place since the capture
+            self.drain()
+            self._capture()
         s = self.n & 1
         first_use = self.n < 2
         with torch.cuda.stream(self.copy_in):

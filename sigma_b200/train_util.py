@@ -27,9 +27,10 @@ def group_weight(module, lr, norm_layer=nn.BatchNorm2d):
     return [dict(params=decay, lr=lr), dict(params=no_decay, weight_decay=0.0, lr=lr)]
 
 
-def make_optimizer(model, lr=6e-5, weight_decay=0.01):
-    """train.py:84-93 with configs/config_MFNet.py:53-59 (AdamW, lr 6e-5, betas (0.9, 0.999), weight decay 0.01)."""
-    return torch.optim.AdamW(group_weight(model, lr), lr=lr, betas=(0.9, 0.999), weight_decay=weight_decay)
+def make_optimizer(model, lr=6e-5, weight_decay=0.01, capturable=False):
+    """train.py:84-93 with configs/config_MFNet.py:53-59 (AdamW, lr 6e-5, betas (0.9, 0.999), weight decay 0.01).
+    capturable=True keeps the step counters on the device so the whole step can live in a CUDA graph."""
+    return torch.optim.AdamW(group_weight(model, lr), lr=lr, betas=(0.9, 0.999), weight_decay=weight_decay, capturable=capturable)
 
 
 def wrap_ddp(model, device_index=None):

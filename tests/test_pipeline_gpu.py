@@ -46,3 +46,31 @@ def test_pipeline_requires_cuda_model():
         model = M.EncoderDecoder(cfg_tiny(64, 96), criterion=None).eval()
     with pytest.raises(RuntimeError):
         InferencePipeline(model, 1, 64, 96)
+
+
+def test_pipeline_recaptures_after_weight_update():
+    """The graph bakes in the pointers of the packed SSM tensors derived from the parameters: after an in-place weight change
+    (load_state_dict) the pipeline must serve the NEW weights, not stale packed copies, and it refuses a model in train mode."""
+    import procedural as P
+    from sigma_b200 import modules as M
+    from sigma_b200.pipeline import InferencePipeline
+    torch.backends.cuda.matmul.allow_tf32 = True
+    H, W, B = 64, 96, 1
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = M.EncoderDecoder(cfg_tiny(H, W), criterion=None).cuda().eval()
+    P.fill_state_dict(model, 3)
+    pipe = InferencePipeline(model, B, H, W)
+    h_rgb, h_x = torch.randn(B, 3, H, W).pin_memory(), torch.randn(B, 3, H, W).pin_memory()
+    out0, out1 = torch.empty(pipe.out_shape).pin_memory(), torch.empty(pipe.out_shape).pin_memory()
+    pipe.submit(h_rgb, h_x, out0)
+    pipe.drain()
+    P.fill_state_dict(model, 4)                      # in-place update of every parameter (incl. x_proj_weight, A_logs, Ds, dt_projs_*)
+    pipe.submit(h_rgb, h_x, out1)
+    pipe.drain()
+    with torch.no_grad():
+        ref = model(h_rgb.cuda(), h_x.cuda()).cpu()
+    assert float((out1 - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max())), "stale weights replayed after load_state_dict"
+    assert float((out1 - out0).abs().max()) > 1e-3
+    model.train()
+    with pytest.raises(RuntimeError):
+        InferencePipeline(model, B, H, W)
