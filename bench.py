@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--width", type=int, default=640)
     ap.add_argument("--num-classes", type=int, default=9)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"],
+                    help="dense projections of the fused path: tf32x3 = fp32-grade products on the tensor cores (error-compensated split, "
+                         "3 tcgen05 MMAs per k-step; torch's default matmul precision, logits within 1e-5 of the reference's); tf32 = "
+                         "one MMA per k-step (torch.backends.cuda.matmul.allow_tf32 = True; logits within ~3e-3)")
     ap.add_argument("--cublas-gemm", action="store_true", help="A/B: dense projections through cuBLAS instead of our tcgen05 GEMM")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-by-batch", action="store_true", help="skip the B = 1..16 sweep appended to the line at N = 1")
@@ -67,6 +71,13 @@ def cfg_of(a):
     return types.SimpleNamespace(backbone=a.model, decoder="MambaDecoder", num_classes=a.num_classes,
                                  image_height=a.height, image_width=a.width, pretrained_model=None, bn_eps=1e-3,
                                  bn_momentum=0.1)
+
+
+def metric_name(a):
+    """BASELINE.json's metric for its own configuration; the same quantity named after the model / size otherwise."""
+    if a.model == "sigma_tiny" and (a.height, a.width) == (480, 640):
+        return "images/sec Sigma-tiny 480x640 fwd"
+    return f"images/sec {a.model} {a.height}x{a.width} fwd"
 
 
 def workload_name(a):
@@ -127,7 +138,7 @@ def run_reference(a):
     t0 = time.perf_counter()
     ips, dt = cpu_reference_images_per_s(a, n * per_step)
     line = {
-        "impl": "reference", "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(ips, 5), "unit": "images/s",
+        "impl": "reference", "metric": metric_name(a), "value": round(ips, 5), "unit": "images/s",
         "n_gpus": a.gpus, "steps": n, "warmup": min(a.warmup, 1), "ms_per_step": round(1e3 * dt / n, 2),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "sample": "1 image per step (bounded sample of the batch)",
@@ -367,7 +378,7 @@ def run_train(a):
         sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
         import selective_scan_cuda_core as ref_ext
         ops.selective_scan_cuda_core_fwd = lambda u, delta, A, Bm, Cm, D=None, bias=None, sp=False, nrows=1, **k: ref_ext.fwd(u, delta, A, Bm, Cm, D, bias, sp, nrows)
-        ops.selective_scan_cuda_core_bwd = lambda u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows=1, **k: ref_ext.bwd(u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows)
+        ops.selective_scan_cuda_core_bwd = lambda u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows=1, **k: ref_ext.bwd(u, delta, A, Bm, Cm, D, bias, dout if dout.stride(-1) == 1 else dout.contiguous(), x, sp, nrows)  # vmamba.py:72-74
     use_graph = a.train_graph and world == 1
     opt = train_util.make_optimizer(model, capturable=use_graph)
     ddp = train_util.wrap_ddp(model, local)
@@ -541,9 +552,9 @@ def main():
     from sigma_b200 import _lib, fused, modules as M
     if a.cublas_gemm:
         fused.USE_TCGEN05_GEMM = False
-    # dense projections run on the tensor cores in TF32 (fp32 storage, fp32 accumulate); the scan is fp32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    torch.backends.cudnn.allow_tf32 = True
+    # dense projections run on the tensor cores (fp32 storage, fp32 accumulate in TMEM), fp32-grade by default; the scan is fp32
+    torch.backends.cuda.matmul.allow_tf32 = a.precision == "tf32"
+    torch.backends.cudnn.allow_tf32 = True      # torch's default, also the reference's: the few cuDNN convs (patch embed, CAB 3x3)
     torch.manual_seed(0)
     import contextlib
     import io
@@ -700,12 +711,15 @@ def main():
     in_bytes = 2 * B * 3 * a.height * a.width * 4
     out_bytes = static_out.numel() * static_out.element_size()
     line = {
-        "metric": "images/sec Sigma-tiny 480x640 fwd", "value": round(dist_util.aggregate_images_per_s(B, world, a.steps, total_ms), 3),
+        "metric": metric_name(a), "value": round(dist_util.aggregate_images_per_s(B, world, a.steps, total_ms), 3),
         "unit": "images/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(total_ms / a.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": f"replicas x{world} (no data-path collective)", "scan_math": "fp32",
-                   "dense_math": "tf32 tensor cores (hand-written tcgen05 GEMM), fp32 accumulate" if fused.USE_TCGEN05_GEMM else "tf32 cuBLAS", "cuda_graph": graph is not None,
+                   "dense_math": ("tf32x3: fp32-grade products on the tensor cores (hand-written tcgen05 GEMM, error-compensated operand split, "
+                                  "3 kind::tf32 MMAs per k-step), fp32 accumulate" if a.precision == "tf32x3" else
+                                  "tf32 tensor cores (hand-written tcgen05 GEMM, 1 MMA per k-step), fp32 accumulate") if fused.USE_TCGEN05_GEMM else "cuBLAS",
+                   "precision": fused.precision(), "cuda_graph": graph is not None,
                    "l2": "256 MiB flush between timed steps",
                    "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},
         "roofline": roofline, "cpu_baseline": cpu, "gpu_baseline": gpu_base, "by_batch": by_batch,

@@ -193,6 +193,14 @@ int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const f
 int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *bias, const float *residual, int64_t ldr,
                       const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream);
 
+/* The same GEMM with fp32-GRADE products on the TF32 tensor pipe ("tf32x3": A·W = A_hi·W_hi + A_lo·W_hi + A_hi·W_lo, x_hi = x with
+ * the low 13 mantissa bits cleared; three tcgen05 MMAs per k-step, activations split in shared memory inside the kernel): what
+ * torch's nn.Linear computes with torch.backends.cuda.matmul.allow_tf32 = False, to ~1e-6 relative.  The weights arrive
+ * pre-split (W_hi, W_lo each (N, K) contiguous): split them once with sigma_split_tf32_fwd.                                  */
+int sigma_linear_tf32x3(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, const float *residual,
+                        int64_t ldr, const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream);
+int sigma_split_tf32_fwd(const float *x, float *hi, float *lo, int64_t n, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * SURVEY.md §8(f) rank 2, first piece: the evaluator's per-batch metric on the device (eval.py:22-29,
  * utils/metric.py:8-15).  pred = argmax over classes of logits (batch, classes, H, W) — the index numpy.argmax

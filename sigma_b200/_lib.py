@@ -48,6 +48,8 @@ SIGNATURES = {
     "sigma_eval_resize_add_fwd": (c_int, [c_void_p] + [c_int] * 7 + [c_void_p, c_int, c_int, c_void_p]),
     "sigma_eval_argmax_hist_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_void_p]),
     "sigma_linear_tf32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sigma_linear_tf32x3": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sigma_split_tf32_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

@@ -165,8 +165,9 @@ int upsample2x_norm_launch(const float *in, const float *gamma, const float *bet
 int pool_avgmax_partial_launch(const float *x, float *partial, int B, long long L, int C, int nslice, cudaStream_t stream);
 int scale_add_launch(const float *a, const float *sa, const float *b, const float *sb, float *out, long long rows,
                      long long rows_per_batch, int C, cudaStream_t stream);
-int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *bias, const float *residual, long long ldr,
-                     const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream);
+int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *W_lo, const float *bias, const float *residual,
+                     long long ldr, const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream);
+int split_tf32_launch(const float *x, float *hi, float *lo, long long n, cudaStream_t stream);
 struct ImagePreParams {
   const unsigned char *src; float *dst; const unsigned char *lsrc; long long *ldst;
   int H0, W0, SH, SW, OH, OW, off_y, off_x, mirror_src, mirror_out, label_pad;
@@ -392,7 +393,24 @@ int sigma_linear_tf32(const float *A, int64_t lda, const float *W, const float *
   SIGMA_CHECK_ARG(al16(A) && al16(W) && al16(C) && al16(bias) && al16(residual) && al16(rscale),
                   "sigma_linear_tf32: pointers must be 16-byte aligned");
   SIGMA_CHECK_ARG(rscale == nullptr || residual != nullptr, "sigma_linear_tf32: rscale without residual");
-  return gemm_tf32_launch(A, lda, W, bias, residual, ldr, rscale, C, ldc, M, N, K, (cudaStream_t)stream);
+  return gemm_tf32_launch(A, lda, W, nullptr, bias, residual, ldr, rscale, C, ldc, M, N, K, (cudaStream_t)stream);
+}
+
+int sigma_linear_tf32x3(const float *A, int64_t lda, const float *W_hi, const float *W_lo, const float *bias, const float *residual,
+                        int64_t ldr, const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream) {
+  SIGMA_CHECK_ARG(A && W_hi && W_lo && C, "sigma_linear_tf32x3: null pointer");
+  SIGMA_CHECK_ARG(M >= 0 && M < (1LL << 31) && N > 0 && K > 0, "sigma_linear_tf32x3: bad sizes M=%lld N=%d K=%d", (long long)M, N, K);
+  SIGMA_CHECK_ARG(K % 4 == 0 && N % 4 == 0 && lda % 4 == 0 && ldc % 4 == 0 && (residual == nullptr || ldr % 4 == 0) && lda >= K && ldc >= N,
+                  "sigma_linear_tf32x3: K, N, lda, ldc, ldr must be multiples of 4 floats");
+  SIGMA_CHECK_ARG(al16(A) && al16(W_hi) && al16(W_lo) && al16(C) && al16(bias) && al16(residual) && al16(rscale),
+                  "sigma_linear_tf32x3: pointers must be 16-byte aligned");
+  SIGMA_CHECK_ARG(rscale == nullptr || residual != nullptr, "sigma_linear_tf32x3: rscale without residual");
+  return gemm_tf32_launch(A, lda, W_hi, W_lo, bias, residual, ldr, rscale, C, ldc, M, N, K, (cudaStream_t)stream);
+}
+
+int sigma_split_tf32_fwd(const float *x, float *hi, float *lo, int64_t n, void *stream) {
+  SIGMA_CHECK_ARG(x && hi && lo && n >= 0, "sigma_split_tf32_fwd: bad arguments");
+  return split_tf32_launch(x, hi, lo, n, (cudaStream_t)stream);
 }
 
 int sigma_image_pre_fwd(const uint8_t *src, const uint8_t *labels, float *out, int64_t *labels_out, int H0, int W0, int SH, int SW,

@@ -11,6 +11,13 @@
 // Persistent CTAs loop over 128 x BN output tiles (BN <= 256, multiple of 16, a runtime value chosen per call) with
 // two TMEM accumulator stages, so the loads and MMAs of the next tile overlap the epilogue of the current one.
 // These GEMMs are HBM-bound at the Sigma shapes (K = 96..1536): what matters is one pass over A and one over C.
+//
+// X3 = true ("tf32x3", sigma_linear_tf32x3): fp32-grade products on the TF32 tensor pipe by error compensation,
+//     A·W = A_hi·W_hi + A_lo·W_hi + A_hi·W_lo  (+ A_lo·W_lo ~ 2^-22, dropped),   x_hi = x with the low 13 mantissa bits cleared.
+// W_hi / W_lo come pre-split from the caller (weights: split once, sigma_split_tf32_fwd); the activations are split in
+// shared memory by four extra warps between the TMA arrival and the MMA issue (hi written in place — exactly representable,
+// so the tensor core's own TF32 conversion is the identity on it — lo into a second tile of the stage), and the issuer
+// launches three MMAs per k-step.  The plain kernel's code is untouched by the template.
 #include <algorithm>
 
 #include "common.cuh"
@@ -23,7 +30,7 @@ constexpr int GM_BK = 32;    // fp32 elements per k-block = one 128-byte swizzle
 constexpr int GM_UK = 8;     // UMMA_K for kind::tf32 (32 bytes)
 
 struct alignas(64) GemmParams {
-  CUtensorMap m_a, m_w, m_c;
+  CUtensorMap m_a, m_w, m_c, m_wlo;
   const float *bias, *residual, *rscale;
   float *C;
   long long ldr, ldc;
@@ -102,16 +109,19 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                : "memory");
 }
 
-__global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
+template <bool X3>
+__global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int BN = p.BN, S = p.stages;
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = BN * GM_BK * 4;
-  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
+  const int half_bytes = a_bytes + ((b_bytes + 1023) & ~1023);   // [A | W] ; X3: a second [A_lo | W_lo] follows
+  const int stage_bytes = X3 ? 2 * half_bytes : half_bytes;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)S * stage_bytes);
   uint64_t *empty = full + S;
   uint64_t *acc_full = empty + S;      // [2]: accumulator stage complete (MMA -> epilogue)
   uint64_t *acc_empty = acc_full + 2;  // [2]: accumulator stage drained (epilogue -> MMA)
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+  uint64_t *split = acc_empty + 2;     // [S] (X3): the activations of the stage are split into hi / lo
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(split + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + GM_BK - 1) / GM_BK;
@@ -124,7 +134,7 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
     tma_prefetch_desc(&p.m_a);
     tma_prefetch_desc(&p.m_w);
     tma_prefetch_desc(&p.m_c);
-    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&split[s], 4); }
     for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 8); }
     fence_mbar_init();
   }
@@ -151,9 +161,10 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
           const int st = (int)(it % S);
           mbar_wait_backoff(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));
           unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
-          mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + b_bytes));
+          mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + (X3 ? 2 : 1) * b_bytes));
           tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);
           tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kb * GM_BK, n0);
+          if (X3) tma_load_2d(sa + half_bytes + a_bytes, &p.m_wlo, &full[st], kb * GM_BK, n0);
         }
       }
     }
@@ -169,16 +180,50 @@ __global__ void __launch_bounds__(320) gemm_tf32_kernel(const __grid_constant__ 
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int st = (int)(it % S);
-          mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+          mbar_wait(X3 ? &split[st] : &full[st], (uint32_t)((it / S) & 1));
           tc_fence_after();
           const unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
           const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sa + a_bytes);
+          if (X3) {
+            const uint64_t dal = umma_desc_sw128(sa + half_bytes), dbl = umma_desc_sw128(sa + half_bytes + a_bytes);
 #pragma unroll
-          for (int k = 0; k < GM_BK / GM_UK; ++k)   // +32 B along K inside the swizzle row = +2 in 16-byte units
-            umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < GM_BK / GM_UK; ++k) {   // small terms first
+              umma_tf32(tmem_d, dal + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+              umma_tf32(tmem_d, da + (uint64_t)(2 * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+              umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < GM_BK / GM_UK; ++k)   // +32 B along K inside the swizzle row = +2 in 16-byte units
+              umma_tf32(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
           umma_commit(&empty[st]);                   // frees the smem slot once these MMAs have read it
         }
         umma_commit(&acc_full[acc]);                 // accumulator of this tile complete
+      }
+    }
+  } else if (X3 && warp >= 10) {
+    // ===== activation splitters (X3): A tile -> (hi in place, lo in the stage's second half), elementwise at the same
+    // swizzled offsets, then the async proxy (tensor core) may read both =====
+    const int t = threadIdx.x - 320;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int st = (int)(it % S);
+        mbar_wait(&full[st], (uint32_t)((it / S) & 1));
+        uint4 *hi = reinterpret_cast<uint4 *>(smem_raw + (size_t)st * stage_bytes);
+        float4 *lo = reinterpret_cast<float4 *>(smem_raw + (size_t)st * stage_bytes + half_bytes);
+#pragma unroll
+        for (int i = 0; i < GM_BM * GM_BK / 4 / 128; ++i) {
+          const uint4 v = hi[t + 128 * i];
+          const uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
+          hi[t + 128 * i] = h;
+          lo[t + 128 * i] = make_float4(__uint_as_float(v.x) - __uint_as_float(h.x), __uint_as_float(v.y) - __uint_as_float(h.y),
+                                        __uint_as_float(v.z) - __uint_as_float(h.z), __uint_as_float(v.w) - __uint_as_float(h.w));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split[st]);
       }
     }
   } else {
@@ -315,9 +360,28 @@ static int make_tmap_c(CUtensorMap *map, const float *base, long long rows, long
   return SIGMA_OK;
 }
 
-int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *bias, const float *residual, long long ldr,
-                     const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream) {
+// x -> (hi = x with the low 13 mantissa bits cleared, lo = x - hi): the operand split of the tf32x3 GEMM, for the weights
+__global__ void split_tf32_kernel(const float *__restrict__ x, float *__restrict__ hi, float *__restrict__ lo, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+int split_tf32_launch(const float *x, float *hi, float *lo, long long n, cudaStream_t stream) {
+  if (n == 0) return SIGMA_OK;
+  split_tf32_kernel<<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(x, hi, lo, n);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+// W_lo == nullptr: plain TF32 (one MMA per k-step); else tf32x3 with W = W_hi
+int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *W_lo, const float *bias, const float *residual,
+                     long long ldr, const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream) {
   if (M == 0) return SIGMA_OK;
+  const bool x3 = W_lo != nullptr;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.bias = bias; p.residual = residual; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
@@ -328,17 +392,19 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   int rc;
   if ((rc = make_tmap_2d_sw128(&p.m_a, A, M, K, lda, GM_BM))) return rc;
   if ((rc = make_tmap_2d_sw128(&p.m_w, W, N, K, K, p.BN))) return rc;
+  if (x3 && (rc = make_tmap_2d_sw128(&p.m_wlo, W_lo, N, K, K, p.BN))) return rc;
   if ((rc = make_tmap_c(&p.m_c, C, M, N, ldc))) return rc;
   const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
-  const int stage_bytes = a_bytes + ((b_bytes + 1023) & ~1023);
-  const int nkb = (K + GM_BK - 1) / GM_BK;
+  const int stage_bytes = (a_bytes + ((b_bytes + 1023) & ~1023)) * (x3 ? 2 : 1);
   p.stages = std::max(2, std::min(8, (192 * 1024) / stage_bytes));
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
-  SIGMA_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const void *kern = x3 ? (const void *)gemm_tf32_kernel<true> : (const void *)gemm_tf32_kernel<false>;
+  SIGMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)((N + p.BN - 1) / p.BN) * ((M + GM_BM - 1) / GM_BM);
   const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
   const unsigned grid = (unsigned)std::min<long long>(total, 148LL * ctas_per_sm);   // persistent CTAs
-  gemm_tf32_kernel<<<grid, 320, smem, stream>>>(p);
+  if (x3) gemm_tf32_kernel<true><<<grid, 448, smem, stream>>>(p);
+  else gemm_tf32_kernel<false><<<grid, 320, smem, stream>>>(p);
   SIGMA_CHECK_LAUNCH();
   return SIGMA_OK;
 }

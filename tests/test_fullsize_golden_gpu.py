@@ -62,7 +62,7 @@ def _check(logits, g, ncls, tag, bar, min_agree, miou_tol, H, W):
 
 
 @pytest.mark.parametrize("which", ["tiny", "small", "base"])
-@pytest.mark.parametrize("path", ["fused_fp32", "fused_tf32", "composed"])
+@pytest.mark.parametrize("path", ["fused_tf32x3", "fused_tf32", "composed"])
 def test_logits_vs_reference_golden_fullsize(which, path):
     tag, backbone, H, W, ncls = CASES[which]
     if not _have(tag):

@@ -35,14 +35,14 @@ def _tol(path, ref):
 
 
 def _ctx(path):
-    """composed: op-level kernels under torch ops; fused_fp32: fused kernels, full-precision projections (torch's default
-    switch, the reference's numerics); fused_tf32: fused kernels with the tcgen05 TF32 GEMM (what bench.py measures)."""
+    """composed: op-level kernels under torch ops; fused_tf32x3: fused kernels, fp32-grade projections on the tensor cores
+    (torch's default switch = the reference's numerics); fused_tf32: the same kernels with one TF32 MMA per k-step."""
     from sigma_b200 import modules as M
     torch.backends.cuda.matmul.allow_tf32 = path == "fused_tf32"
     return M.composed_path(path == "composed")
 
 
-PATHS = ["composed", "fused_fp32", "fused_tf32"]
+PATHS = ["composed", "fused_tf32x3", "fused_tf32"]
 
 
 @pytest.mark.parametrize("path", PATHS)
