@@ -100,6 +100,19 @@ def linear(x2d, weight, bias=None, out=None, residual=None, rscale=None, kind="d
     return out
 
 
+def patch_embed(conv, x):
+    """The patch-embedding convolution (vmamba.py:1967-1971: Conv2d(3, C, kernel 4, stride 4)) as a GEMM: non-overlapping
+    patches make im2col a pure re-ordering, (B, 3, H, W) -> (B·H/4·W/4, 3·4·4) rows in the (c, ky, kx) order of the conv
+    weight, then the tcgen05 GEMM with the bias in its epilogue.  Returns (B, H/4, W/4, C) channels-last.  None when the
+    convolution is not of that form (caller falls back to cuDNN)."""
+    p = conv.kernel_size[0]
+    B, Cin, H, W = x.shape
+    if conv.kernel_size != (p, p) or conv.stride != (p, p) or conv.padding != (0, 0) or conv.groups != 1 or H % p or W % p or (Cin * p * p) % 4:
+        return None
+    cols = x.reshape(B, Cin, H // p, p, W // p, p).permute(0, 2, 4, 1, 3, 5).reshape(B * (H // p) * (W // p), Cin * p * p)
+    return linear(cols, conv.weight.reshape(conv.out_channels, Cin * p * p), conv.bias, kind="patch_embed").view(B, H // p, W // p, conv.out_channels)
+
+
 def dwconv3x3_silu(x, x_row_stride, x_batch_stride, conv, out, out_batch_stride, batch, H, W, D):
     _lib.check(_lib.lib().sigma_dwconv3x3_silu_fwd(_p(x), x_row_stride, x_batch_stride, _p(conv.weight), _p(conv.bias),
                                                    _p(out), out_batch_stride, batch, H, W, D, _stream()),

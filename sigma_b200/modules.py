@@ -627,8 +627,9 @@ class Backbone_VSSM(VSSM):
         if _fused_ok(x):
             from . import fused
             fused_ln = fused.ln_nhwc
-            # channels_last input -> cuDNN's NHWC kernel -> the (B,H,W,C) view below is contiguous (no transposing copy)
-            x = self.patch_embed[0](x.contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1)
+            pe = fused.patch_embed(self.patch_embed[0], x)      # 4x4 / stride-4 conv = re-ordering + our GEMM (no cuDNN)
+            # otherwise: channels_last input -> cuDNN's NHWC kernel -> the (B,H,W,C) view is contiguous (no transposing copy)
+            x = pe if pe is not None else self.patch_embed[0](x.contiguous(memory_format=torch.channels_last)).permute(0, 2, 3, 1)
             x = fused_ln(self.patch_embed[2], x) if isinstance(self.patch_embed[2], nn.LayerNorm) else x.contiguous()
         else:
             x = self.patch_embed(x)

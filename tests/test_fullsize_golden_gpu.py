@@ -62,16 +62,18 @@ def _check(logits, g, ncls, tag, bar, min_agree, miou_tol, H, W):
 
 
 @pytest.mark.parametrize("which", ["tiny", "small", "base"])
-@pytest.mark.parametrize("path", ["fused_tf32x3", "fused_tf32", "composed"])
+@pytest.mark.parametrize("path", ["fused_tf32x3", "fused_tf32x3_cudnn_tf32", "fused_tf32", "composed"])
 def test_logits_vs_reference_golden_fullsize(which, path):
     tag, backbone, H, W, ncls = CASES[which]
     if not _have(tag):
         pytest.skip(f"{tag}.npz not generated")
-    if path == "composed" and which != "tiny":
-        pytest.skip("composed path at this size is covered by tiny; small/base run the fused path")
+    if path in ("composed", "fused_tf32x3_cudnn_tf32") and which != "tiny":
+        pytest.skip("covered at the tiny size; small/base run the two fused precisions")
     from sigma_b200 import fused, modules as M
     torch.backends.cuda.matmul.allow_tf32 = path == "fused_tf32"    # the fused path's precision follows torch's switch
-    torch.backends.cudnn.allow_tf32 = False
+    # "fused_tf32x3_cudnn_tf32" is EXACTLY bench.py's default configuration: fp32-grade projections, and cuDNN left at torch's
+    # (and the reference's) default for the three library convolutions still on the path (patch embed, the CAB's 3x3 pair)
+    torch.backends.cudnn.allow_tf32 = path == "fused_tf32x3_cudnn_tf32"
     g = golden(tag)
     model = _model(backbone, H, W, ncls)
     rgb = P.randn(SEED, tag + "/rgb", (1, 3, H, W)).cuda()
