@@ -201,6 +201,14 @@ int sigma_linear_tf32x3(const float *A, int64_t lda, const float *W_hi, const fl
                         int64_t ldr, const float *rscale, float *C, int64_t ldc, int64_t M, int N, int K, void *stream);
 int sigma_split_tf32_fwd(const float *x, float *hi, float *lo, int64_t n, void *stream);
 
+/* Dense 3x3 convolution (pad 1, stride 1) of the ChannelAttentionBlock (vmamba.py:1749-1752), channels-last, as an implicit GEMM on
+ * the same tcgen05 kernel: y (batch, H, W, Cout) = conv(x (batch, H, W, Cin), w9) + bias, act = 1 applies the exact (erf) GELU of
+ * nn.GELU() in the epilogue.  w9 = the nn.Conv2d weight (Cout, Cin, 3, 3) re-ordered to (3·3, Cout, Cin); every tap's input patch
+ * is one shifted 4-D TMA box whose out-of-bounds fill is the zero padding.  w9_lo == NULL: one TF32 MMA per k-step; otherwise
+ * tf32x3 with (w9, w9_lo) = sigma_split_tf32_fwd of the re-ordered weight.  Cin, Cout % 4 == 0.                              */
+int sigma_conv3x3_tf32(const float *x, const float *w9, const float *w9_lo, const float *bias, int act, float *y, int batch, int H, int W,
+                       int Cin, int Cout, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * SURVEY.md §8(f) rank 2, first piece: the evaluator's per-batch metric on the device (eval.py:22-29,
  * utils/metric.py:8-15).  pred = argmax over classes of logits (batch, classes, H, W) — the index numpy.argmax

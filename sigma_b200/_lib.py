@@ -49,6 +49,7 @@ SIGNATURES = {
     "sigma_eval_argmax_hist_fwd": (c_int, [c_void_p] * 5 + [c_int, c_int64, c_void_p]),
     "sigma_linear_tf32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
     "sigma_linear_tf32x3": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]),
+    "sigma_conv3x3_tf32": (c_int, [c_void_p] * 4 + [c_int, c_void_p] + [c_int] * 5 + [c_void_p]),
     "sigma_split_tf32_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 

@@ -168,6 +168,8 @@ int scale_add_launch(const float *a, const float *sa, const float *b, const floa
 int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *W_lo, const float *bias, const float *residual,
                      long long ldr, const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream);
 int split_tf32_launch(const float *x, float *hi, float *lo, long long n, cudaStream_t stream);
+int conv3x3_tf32_launch(const float *x, const float *W9, const float *W9_lo, const float *bias, int act, float *y, int B, int H, int W,
+                        int Cin, int Cout, cudaStream_t stream);
 struct ImagePreParams {
   const unsigned char *src; float *dst; const unsigned char *lsrc; long long *ldst;
   int H0, W0, SH, SW, OH, OW, off_y, off_x, mirror_src, mirror_out, label_pad;
@@ -406,6 +408,16 @@ int sigma_linear_tf32x3(const float *A, int64_t lda, const float *W_hi, const fl
                   "sigma_linear_tf32x3: pointers must be 16-byte aligned");
   SIGMA_CHECK_ARG(rscale == nullptr || residual != nullptr, "sigma_linear_tf32x3: rscale without residual");
   return gemm_tf32_launch(A, lda, W_hi, W_lo, bias, residual, ldr, rscale, C, ldc, M, N, K, (cudaStream_t)stream);
+}
+
+int sigma_conv3x3_tf32(const float *x, const float *w9, const float *w9_lo, const float *bias, int act, float *y, int batch, int H, int W,
+                       int Cin, int Cout, void *stream) {
+  SIGMA_CHECK_ARG(x && w9 && y, "sigma_conv3x3_tf32: null pointer");
+  SIGMA_CHECK_ARG(batch >= 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0 && Cin % 4 == 0 && Cout % 4 == 0,
+                  "sigma_conv3x3_tf32: bad sizes (Cin=%d, Cout=%d must be multiples of 4)", Cin, Cout);
+  SIGMA_CHECK_ARG(act == 0 || act == 1, "sigma_conv3x3_tf32: act must be 0 (none) or 1 (GELU)");
+  SIGMA_CHECK_ARG(al16(x) && al16(w9) && al16(w9_lo) && al16(bias) && al16(y), "sigma_conv3x3_tf32: pointers must be 16-byte aligned");
+  return conv3x3_tf32_launch(x, w9, w9_lo, bias, act, y, batch, H, W, Cin, Cout, (cudaStream_t)stream);
 }
 
 int sigma_split_tf32_fwd(const float *x, float *hi, float *lo, int64_t n, void *stream) {

@@ -14,10 +14,18 @@
 //
 // X3 = true ("tf32x3", sigma_linear_tf32x3): fp32-grade products on the TF32 tensor pipe by error compensation,
 //     A·W = A_hi·W_hi + A_lo·W_hi + A_hi·W_lo  (+ A_lo·W_lo ~ 2^-22, dropped),   x_hi = x with the low 13 mantissa bits cleared.
+// CONV = true (sigma_conv3x3_tf32): the SAME kernel as an implicit-GEMM 3x3 convolution (pad 1, stride 1) over a channels-last
+// (B, H, W, Cin) tensor: an M tile is an 8 x 16 pixel patch, the K loop runs over 9 taps x Cin blocks, and the A tile of tap
+// (dy, dx) is ONE 4-D TMA box of the input shifted by (dy-1, dx-1) whose out-of-bounds fill is the zero padding (no im2col
+// tensor); weights are (9, Cout, Cin); bias and an optional exact GELU are fused in the epilogue, whose per-warp store box is
+// {32 channels, 16, 2 rows, 1}.  Replaces the ChannelAttentionBlock's two dense convolutions (vmamba.py:1749-1752).
+//
 // W_hi / W_lo come pre-split from the caller (weights: split once, sigma_split_tf32_fwd); the activations are split in
 // shared memory by four extra warps between the TMA arrival and the MMA issue (hi written in place — exactly representable,
 // so the tensor core's own TF32 conversion is the identity on it — lo into a second tile of the stage), and the issuer
 // launches three MMAs per k-step.  The plain kernel's code is untouched by the template.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -35,11 +43,26 @@ struct alignas(64) GemmParams {
   float *C;
   long long ldr, ldc;
   int M, N, K, BN, stages, tmem_cols;
+  int x3_keep_hi;   // X3: 1 = the splitter also rewrites the activations' hi part in place (needed only if the tensor core ROUNDS to TF32)
+  int cH, cW, tiles_w, tiles_hw, kbc, act;   // CONV: image size, 8x16 patches per row / per image, Cin blocks per tap, activation
 };
+
+constexpr int CV_TH = 8, CV_TW = 16;   // pixel patch of one M tile (8 x 16 = GM_BM)
 
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+__device__ __forceinline__ void tma_load_4d_g(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_g(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)map),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 
@@ -109,7 +132,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, const void 
                : "memory");
 }
 
-template <bool X3>
+template <bool X3, bool CONV>
 __global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int BN = p.BN, S = p.stages;
@@ -124,9 +147,9 @@ __global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(split + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (p.K + GM_BK - 1) / GM_BK;
+  const int nkb = CONV ? 9 * p.kbc : (p.K + GM_BK - 1) / GM_BK;
   const int num_n = (p.N + BN - 1) / BN;
-  const int num_m = (p.M + GM_BM - 1) / GM_BM;
+  const int num_m = CONV ? p.M : (p.M + GM_BM - 1) / GM_BM;      // CONV: p.M counts pixel patches
   const long long total = (long long)num_m * num_n;
   const int acc_cols = p.tmem_cols >> 1;   // columns per accumulator stage
 
@@ -162,9 +185,19 @@ __global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_
           mbar_wait_backoff(&empty[st], (uint32_t)(((it / S) & 1) ^ 1));
           unsigned char *sa = smem_raw + (size_t)st * stage_bytes;
           mbar_arrive_expect_tx(&full[st], (uint32_t)(a_bytes + (X3 ? 2 : 1) * b_bytes));
-          tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);
-          tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kb * GM_BK, n0);
-          if (X3) tma_load_2d(sa + half_bytes + a_bytes, &p.m_wlo, &full[st], kb * GM_BK, n0);
+          if (CONV) {
+            const int mt = (int)(tile / num_n);
+            const int b = mt / p.tiles_hw, r = mt - b * p.tiles_hw, ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+            const int tap = kb / p.kbc, kc = kb - tap * p.kbc, dy = tap / 3, dx = tap - 3 * dy;
+            // the tap's input patch: shifted by (dy-1, dx-1); rows / columns outside the image arrive as zeros = the padding
+            tma_load_4d_g(sa, &p.m_a, &full[st], kc * GM_BK, tx * CV_TW + dx - 1, ty * CV_TH + dy - 1, b);
+            tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kc * GM_BK, tap * p.N + n0);
+            if (X3) tma_load_2d(sa + half_bytes + a_bytes, &p.m_wlo, &full[st], kc * GM_BK, tap * p.N + n0);
+          } else {
+            tma_load_2d(sa, &p.m_a, &full[st], kb * GM_BK, m0);
+            tma_load_2d(sa + a_bytes, &p.m_w, &full[st], kb * GM_BK, n0);
+            if (X3) tma_load_2d(sa + half_bytes + a_bytes, &p.m_wlo, &full[st], kb * GM_BK, n0);
+          }
         }
       }
     }
@@ -217,7 +250,7 @@ __global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_
         for (int i = 0; i < GM_BM * GM_BK / 4 / 128; ++i) {
           const uint4 v = hi[t + 128 * i];
           const uint4 h = make_uint4(v.x & 0xFFFFE000u, v.y & 0xFFFFE000u, v.z & 0xFFFFE000u, v.w & 0xFFFFE000u);
-          hi[t + 128 * i] = h;
+          if (p.x3_keep_hi) hi[t + 128 * i] = h;
           lo[t + 128 * i] = make_float4(__uint_as_float(v.x) - __uint_as_float(h.x), __uint_as_float(v.y) - __uint_as_float(h.y),
                                         __uint_as_float(v.z) - __uint_as_float(h.z), __uint_as_float(v.w) - __uint_as_float(h.w));
         }
@@ -241,8 +274,8 @@ __global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_
       const int m0 = (int)(tile / num_n) * GM_BM, n0 = (int)(tile % num_n) * BN;
       const int acc = (int)(tc & 1);
       const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
-      const float *rrow = (p.residual && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;
+      const bool row_ok = CONV ? false : row < p.M;
+      const float *rrow = (!CONV && p.residual && row_ok) ? p.residual + (long long)row * p.ldr : nullptr;
       // the residual row chunk is fetched one chunk ahead (the first one before the accumulator is even ready): a
       // thread-per-row read is 32 sectors per request and would otherwise sit between tcgen05.ld and the store
       float4 rpre[8];
@@ -286,12 +319,22 @@ __global__ void __launch_bounds__(X3 ? 448 : 320) gemm_tf32_kernel(const __grid_
               }
             }
           }
+          if (CONV && p.act == 1) {   // nn.GELU() (exact, erf)
+            o.x = 0.5f * o.x * (1.f + erff(o.x * 0.70710678118654752f)); o.y = 0.5f * o.y * (1.f + erff(o.y * 0.70710678118654752f));
+            o.z = 0.5f * o.z * (1.f + erff(o.z * 0.70710678118654752f)); o.w = 0.5f * o.w * (1.f + erff(o.w * 0.70710678118654752f));
+          }
           dst[q ^ (lane & 7)] = o;
         }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(&p.m_c, stage_c, n, m0 + quarter * 32);
+          if (CONV) {   // this warp's 32 rows = patch rows 2·quarter, 2·quarter + 1 (16 pixels each)
+            const int mt = (int)(tile / num_n);
+            const int b = mt / p.tiles_hw, r = mt - b * p.tiles_hw, ty = r / p.tiles_w, tx = r - ty * p.tiles_w;
+            tma_store_4d_g(&p.m_c, stage_c, n, tx * CV_TW, ty * CV_TH + 2 * quarter, b);
+          } else {
+            tma_store_2d(&p.m_c, stage_c, n, m0 + quarter * 32);
+          }
           tma_store_commit();
         }
       }
@@ -377,6 +420,13 @@ int split_tf32_launch(const float *x, float *hi, float *lo, long long n, cudaStr
   return SIGMA_OK;
 }
 
+// SIGMA_X3_KEEP_HI=0: the activation splitter does not rewrite the hi part (valid when kind::tf32 TRUNCATES its fp32 operands,
+// which the x3 parity tests decide on the hardware); default 1 = always safe.
+static int x3_keep_hi() {
+  static const int v = [] { const char *e = getenv("SIGMA_X3_KEEP_HI"); return e ? atoi(e) : 1; }();
+  return v;
+}
+
 // W_lo == nullptr: plain TF32 (one MMA per k-step); else tf32x3 with W = W_hi
 int gemm_tf32_launch(const float *A, long long lda, const float *W, const float *W_lo, const float *bias, const float *residual,
                      long long ldr, const float *rscale, float *C, long long ldc, long long M, int N, int K, cudaStream_t stream) {
@@ -384,6 +434,7 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   const bool x3 = W_lo != nullptr;
   GemmParams p;
   memset(&p, 0, sizeof(p));
+  p.x3_keep_hi = x3_keep_hi();
   p.bias = bias; p.residual = residual; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
   p.M = (int)M; p.N = N; p.K = K;
   p.BN = pick_bn(N);
@@ -398,13 +449,65 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   const int stage_bytes = (a_bytes + ((b_bytes + 1023) & ~1023)) * (x3 ? 2 : 1);
   p.stages = std::max(2, std::min(8, (192 * 1024) / stage_bytes));
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 /*barriers*/ + 8 * 4096 /*epilogue staging*/;
-  const void *kern = x3 ? (const void *)gemm_tf32_kernel<true> : (const void *)gemm_tf32_kernel<false>;
+  const void *kern = x3 ? (const void *)gemm_tf32_kernel<true, false> : (const void *)gemm_tf32_kernel<false, false>;
   SIGMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long total = (long long)((N + p.BN - 1) / p.BN) * ((M + GM_BM - 1) / GM_BM);
   const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
   const unsigned grid = (unsigned)std::min<long long>(total, 148LL * ctas_per_sm);   // persistent CTAs
-  if (x3) gemm_tf32_kernel<true><<<grid, 448, smem, stream>>>(p);
-  else gemm_tf32_kernel<false><<<grid, 320, smem, stream>>>(p);
+  if (x3) gemm_tf32_kernel<true, false><<<grid, 448, smem, stream>>>(p);
+  else gemm_tf32_kernel<false, false><<<grid, 320, smem, stream>>>(p);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+int make_tmap_generic(CUtensorMap *map, CUtensorMapDataType dtype, int rank, const void *base, const uint64_t *dims,
+                      const uint64_t *strides_bytes, const uint32_t *box, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo);   // scan_op_tma.cu
+
+// 3x3 convolution, pad 1, stride 1, channels-last: y (B,H,W,Cout) = conv(x (B,H,W,Cin), W9 (9, Cout, Cin)) + bias, optional GELU.
+// W9_lo == nullptr: plain TF32; else tf32x3 with W9 = W9_hi.
+int conv3x3_tf32_launch(const float *x, const float *W9, const float *W9_lo, const float *bias, int act, float *y, int B, int H, int W,
+                        int Cin, int Cout, cudaStream_t stream) {
+  if (B == 0) return SIGMA_OK;
+  const bool x3 = W9_lo != nullptr;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.x3_keep_hi = x3_keep_hi();
+  p.bias = bias; p.C = y;
+  p.N = Cout; p.K = Cin;
+  p.cH = H; p.cW = W; p.act = act;
+  p.tiles_w = (W + CV_TW - 1) / CV_TW;
+  p.tiles_hw = p.tiles_w * ((H + CV_TH - 1) / CV_TH);
+  p.M = B * p.tiles_hw;
+  p.kbc = (Cin + GM_BK - 1) / GM_BK;
+  p.BN = pick_bn(Cout);
+  p.tmem_cols = 2 * (p.BN <= 16 ? 16 : p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256);
+  if (p.tmem_cols < 32) p.tmem_cols = 32;
+  int rc;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t box[4] = {(uint32_t)GM_BK, (uint32_t)CV_TW, (uint32_t)CV_TH, 1};
+    if ((rc = make_tmap_generic(&p.m_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B))) return rc;
+    uint64_t dimc[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strc[3] = {(uint64_t)Cout * 4, (uint64_t)W * Cout * 4, (uint64_t)H * W * Cout * 4};
+    uint32_t boxc[4] = {32, (uint32_t)CV_TW, 2, 1};
+    if ((rc = make_tmap_generic(&p.m_c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dimc, strc, boxc, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE))) return rc;
+  }
+  if ((rc = make_tmap_2d_sw128(&p.m_w, W9, 9LL * Cout, Cin, Cin, p.BN))) return rc;
+  if (x3 && (rc = make_tmap_2d_sw128(&p.m_wlo, W9_lo, 9LL * Cout, Cin, Cin, p.BN))) return rc;
+  const int a_bytes = GM_BM * GM_BK * 4, b_bytes = p.BN * GM_BK * 4;
+  const int stage_bytes = (a_bytes + ((b_bytes + 1023) & ~1023)) * (x3 ? 2 : 1);
+  p.stages = std::max(2, std::min(8, (192 * 1024) / stage_bytes));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 8 * 4096;
+  const void *kern = x3 ? (const void *)gemm_tf32_kernel<true, true> : (const void *)gemm_tf32_kernel<false, true>;
+  SIGMA_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const long long total = (long long)((Cout + p.BN - 1) / p.BN) * p.M;
+  const int ctas_per_sm = std::max(1, std::min(std::min(2, 512 / p.tmem_cols), (int)((220 * 1024) / (smem + 1024))));
+  const unsigned grid = (unsigned)std::min<long long>(total, 148LL * ctas_per_sm);
+  if (x3) gemm_tf32_kernel<true, true><<<grid, 448, smem, stream>>>(p);
+  else gemm_tf32_kernel<false, true><<<grid, 320, smem, stream>>>(p);
   SIGMA_CHECK_LAUNCH();
   return SIGMA_OK;
 }

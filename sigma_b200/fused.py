@@ -113,6 +113,37 @@ def patch_embed(conv, x):
     return linear(cols, conv.weight.reshape(conv.out_channels, Cin * p * p), conv.bias, kind="patch_embed").view(B, H // p, W // p, conv.out_channels)
 
 
+_W9 = {}   # id(conv.weight) -> (weakref, version, w9): the (9, Cout, Cin) re-ordering of a 3x3 conv weight
+
+
+def conv3x3(x, conv, gelu=False):
+    """Dense 3x3 convolution (pad 1) + bias (+ exact GELU) on a channels-last (B, H, W, Cin) tensor through the implicit-GEMM
+    variant of the tcgen05 kernel (sigma_conv3x3_tf32); precision as linear().  Returns (B, H, W, Cout), or None when the
+    convolution is not of that form (caller falls back to cuDNN)."""
+    import weakref
+    if conv.kernel_size != (3, 3) or conv.stride != (1, 1) or conv.padding != (1, 1) or conv.dilation != (1, 1) or conv.groups != 1 \
+            or conv.in_channels % 4 or conv.out_channels % 4 or not USE_TCGEN05_GEMM:
+        return None
+    x = x.contiguous()
+    B, H, W, Cin = x.shape
+    w = conv.weight
+    ent = _W9.get(id(w))
+    if ent is None or ent[0]() is not w or ent[1] != w._version:
+        key = id(w)
+        ent = (weakref.ref(w, lambda _r, k=key: _W9.pop(k, None)), w._version,
+               w.detach().permute(2, 3, 0, 1).reshape(9 * conv.out_channels, Cin).contiguous())
+        _W9[key] = ent
+    w9 = ent[2]
+    y = torch.empty((B, H, W, conv.out_channels), dtype=torch.float32, device=x.device)
+    if precision() == "tf32":
+        hi, lo = w9, None
+    else:
+        hi, lo = _split_weight(w9)
+    rc = _lib.lib().sigma_conv3x3_tf32(_p(x), _p(hi), _p(lo), _p(conv.bias), 1 if gelu else 0, _p(y), B, H, W, Cin, conv.out_channels, _stream())
+    _lib.check(rc, "sigma_conv3x3_tf32")
+    return y
+
+
 def dwconv3x3_silu(x, x_row_stride, x_batch_stride, conv, out, out_batch_stride, batch, H, W, D):
     _lib.check(_lib.lib().sigma_dwconv3x3_silu_fwd(_p(x), x_row_stride, x_batch_stride, _p(conv.weight), _p(conv.bias),
                                                    _p(out), out_batch_stride, batch, H, W, D, _stream()),
@@ -350,8 +381,12 @@ def cvss_decoder_block(blk, x):
     x1 = ss2d(blk.op, xn, residual=x, rscale=blk.scale1)            # x·scale1 + SS2D(LN(x)) in the GEMM epilogue
     xn2 = layernorm(x1.view(-1, C), blk.norm2).view(B, H, W, C)
     cab = blk.conv_blk.cab
-    t = cab[2](cab[1](cab[0](xn2.permute(0, 3, 1, 2))))            # conv3x3 -> GELU -> conv3x3 on a channels_last view
-    t = t.permute(0, 2, 3, 1).contiguous()                           # (B,H,W,C); no copy when cuDNN kept channels_last
+    t = None
+    if isinstance(cab[1], torch.nn.GELU) and getattr(cab[1], "approximate", "none") == "none":
+        h1 = conv3x3(xn2, cab[0], gelu=True)                         # conv3x3 + bias + GELU: implicit GEMM on the tcgen05 kernel
+        t = conv3x3(h1, cab[2]) if h1 is not None else None
+    if t is None:                                                    # other conv forms: cuDNN on a channels_last view
+        t = cab[2](cab[1](cab[0](xn2.permute(0, 3, 1, 2)))).permute(0, 2, 3, 1).contiguous()
     avg, mx = pool_avgmax(t)
     fc = cab[3].fc
     attn = torch.sigmoid(fc(avg.view(B, C, 1, 1)) + fc(mx.view(B, C, 1, 1))).view(B, C).contiguous()

@@ -266,3 +266,29 @@ def test_tcgen05_tf32_gemm(M, N, K, extras, mode):
         fused.linear(big[:, :K], c(Wt), None, out=out[:, :N])
         ref2 = A.double() @ Wt.double().t()
         assert float((out[:, :N].cpu().double() - ref2).abs().max()) < bound and float(out[:, N:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,gelu", [(2, 30, 40, 96, 32, True), (1, 15, 20, 32, 96, False), (3, 9, 17, 128, 384, False),
+                                                 (1, 60, 80, 192, 64, True), (2, 8, 16, 64, 192, False), (1, 1, 5, 32, 32, True)])
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+def test_tcgen05_conv3x3_implicit_gemm(B, H, W, Cin, Cout, gelu, mode):
+    """sigma_conv3x3_tf32 (3x3 conv as 9 shifted TMA boxes x Cin blocks on the tcgen05 kernel; zero padding = TMA out-of-bounds
+    fill; bias + exact GELU in the epilogue) vs torch's conv2d in fp64, ragged image sizes included."""
+    from sigma_b200 import fused
+    torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+    tag = f"conv/{B}/{H}/{W}/{Cin}/{Cout}"
+    conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1)
+    x = P.randn(S, tag + "/x", (B, H, W, Cin))
+    with torch.no_grad():
+        conv.weight.copy_(P.randn(S, tag + "/w", (Cout, Cin, 3, 3), (9 * Cin) ** -0.5))
+        conv.bias.copy_(P.randn(S, tag + "/b", (Cout,), 0.2))
+        ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), conv.weight.double(), conv.bias.double(), padding=1)
+        if gelu:
+            ref = torch.nn.functional.gelu(ref)
+        ref = ref.permute(0, 2, 3, 1)
+        got = fused.conv3x3(x.cuda(), conv.cuda(), gelu=gelu)
+    assert got is not None and tuple(got.shape) == (B, H, W, Cout)
+    mag = float(torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).abs().double(), conv.weight.abs().double().cpu(), padding=1).max())
+    bound = (2.5e-3 if mode == "tf32" else 4e-6) * mag + 1e-5
+    err = float((got.cpu().double() - ref).abs().max())
+    assert err < bound, f"{tag} {mode}: max abs err {err:.3e} > {bound:.3e}"
