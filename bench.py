@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--scan-impl", default="sigma", choices=["sigma", "ref_ext"],
                     help="train mode: ref_ext swaps ONLY the native op for the reference's own CUDA extension (baseline/_ref) under the "
                          "same composition = the reference's training step on this box (the GPU baseline of the training arm)")
+    ap.add_argument("--ddp-default-buckets", action="store_true",
+                    help="train mode: torch DDP's default 25 MB buckets exactly as train.py:103-108 (default here: one aliasing bucket, see train_util.wrap_ddp)")
     ap.add_argument("--train-graph", action="store_true", help="train mode, N = 1: capture the whole step (fwd + bwd + AdamW) in one CUDA graph")
     ap.add_argument("--model", default="sigma_tiny")
     ap.add_argument("--height", type=int, default=480)
@@ -381,7 +383,7 @@ def run_train(a):
         ops.selective_scan_cuda_core_bwd = lambda u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows=1, **k: ref_ext.bwd(u, delta, A, Bm, Cm, D, bias, dout if dout.stride(-1) == 1 else dout.contiguous(), x, sp, nrows)  # vmamba.py:72-74
     use_graph = a.train_graph and world == 1
     opt = train_util.make_optimizer(model, capturable=use_graph)
-    ddp = train_util.wrap_ddp(model, local)
+    ddp = train_util.wrap_ddp(model, local, single_bucket=not a.ddp_default_buckets)
     step_fn = train_util.TrainStep(ddp, opt, amp_dtype=torch.bfloat16 if a.amp == "bf16" else None)
     B = a.batch
     g = torch.Generator().manual_seed(dist_util.shard_seed(1234, rank))
@@ -516,7 +518,8 @@ def run_train(a):
         "dtype": "bf16 autocast dense + f32 scan" if a.amp == "bf16" else "f32 (tf32 dense)", "data": "synthetic",
         "config": {"workload": f"{a.model} train step, synthetic RGB-X {a.height}x{a.width}, {a.num_classes} classes, CE loss, AdamW lr 6e-5 wd 0.01",
                    "batch_per_gpu": B, "global_batch": B * world,
-                   "parallelism": f"DDP x{world} (NCCL all-reduce of {gb / 1e6:.0f} MB fp32 gradients per step)" if world > 1 else "single GPU",
+                   "parallelism": (f"DDP x{world} (NCCL all-reduce of {gb / 1e6:.0f} MB fp32 gradients per step, "
+                                   + ("default 25 MB buckets" if a.ddp_default_buckets else "one bucket aliasing .grad") + ")") if world > 1 else "single GPU",
                    "path": "composed (torch autograd over sigma_scan_fwd / sigma_scan_bwd)" if a.scan_impl == "sigma" else
                            "GPU BASELINE: the same composition over the reference's own selective_scan_cuda_core (rebuilt for sm_100a)",
                    "scan_impl": a.scan_impl, "cuda_graph": graph_note, "l2": "256 MiB flush between timed steps",
