@@ -50,7 +50,7 @@ elif which == "conv":
     conv = torch.nn.Conv2d(96, 32, 3, 1, 1).cuda()
     x = torch.randn(16, 120, 160, 96, device="cuda", generator=g)
     for tf32 in (True, False):
-        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
         for _ in range(2):
             fused.conv3x3(x, conv, gelu=True)
 torch.cuda.synchronize()

@@ -505,12 +505,10 @@ int scan_op_bwd_tma(const void *u, const void *delta, const float *A, const void
   p.ctiles_per_group = p.dpg / p.DT;
   p.ntiles = ntiles;
   p.nhs = (L + OPT_HS_POS - 1) / OPT_HS_POS;
-  // L-segments when the grid leaves SM sub-partitions idle.  The reverse summaries are a cheap extra sweep (no h, no
-  // reductions), so the backward keeps gaining up to ~8 warps per sub-partition (profiles/r02_op_split_sweep.txt).
+  // L-segments: the reverse summaries are a cheap extra sweep (no h, no reductions: ~0.3 of the main sweep), so fill whole
+  // waves of the resident CTA slots (2 x 128-thread CTAs per SM at d_state 16, ~5 x 64-thread CTAs below)
   const int lpc = NP >= 16 ? 2 : 1;
-  const long long warps = (long long)batch * (dim / 32) * lpc, fullm = 148LL * 4;
-  int nsplit = 1;
-  if (warps < 4 * fullm) nsplit = (int)std::min<long long>((8 * fullm + warps - 1) / warps, kBwdMaxSplit);
+  int nsplit = pick_segments((long long)batch * G * p.ctiles_per_group, ntiles, 148LL * (lpc == 2 ? 2 : 5), 1.3, kBwdMaxSplit);
   if (force_split > 0) nsplit = std::min(force_split, kBwdMaxSplit);
   int tps = std::max(1, (ntiles + nsplit - 1) / nsplit);
   p.tiles_per_split = tps;

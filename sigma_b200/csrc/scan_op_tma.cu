@@ -302,6 +302,21 @@ size_t scan_op_tma_workspace_bytes(int batch, int dim, int dstate) {
   return (size_t)batch * dim * kOpMaxSplit * 2 * NP * sizeof(float);
 }
 
+// Number of L-segments minimising  waves x (tiles per segment + fixed) x passes  over 1..max_split: `slots` = CTAs resident on the
+// whole GPU, `pass_factor` = cost of summary + apply relative to one unsplit sweep.
+int pick_segments(long long ctas_base, int ntiles, long long slots, double pass_factor, int max_split) {
+  double best = 1e300;
+  int best_n = 1;
+  for (int n = 1; n <= std::min(max_split, ntiles); ++n) {
+    const int tps = (ntiles + n - 1) / n, ne = (ntiles + tps - 1) / tps;
+    if (ne != n) continue;
+    const long long waves = (ctas_base * ne + slots - 1) / slots;
+    const double cost = (double)waves * (tps + 3) * (ne > 1 ? pass_factor : 1.0);
+    if (cost < best * 0.97) { best = cost; best_n = ne; }   // a larger count must win by > 3 %
+  }
+  return best_n;
+}
+
 template <typename T>
 bool scan_op_tma_eligible(const void *u, const void *delta, const void *B, const void *C, const void *out, int dim, int L,
                           int N, int G, const sigma_scan_strides &s) {
@@ -360,14 +375,13 @@ int scan_op_fwd_tma(const void *u, const void *delta, const float *A, const void
   p.nchunks = (L + 2047) / 2048;
   p.nhs = (L + OPT_HS_POS - 1) / OPT_HS_POS;
 
-  // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY) when the unsplit grid cannot fill the 148 x 4 SM sub-partitions: a
-  // second pass repeats the exponentials, so only below one warp per sub-partition; then ~4 warps per sub-partition win for
-  // every d_state (measured on B200, profiles/r02_op_split_sweep.txt: 192 warps of d_state 16 -> 16 segments 1.62 ms, 7: 1.96).  Segments need not end on the 2048-position chunk boundaries of
-  // `x`: a segment that crosses one writes that chunk's state itself (true h, prefix product = carry-in x local).
-  const long long warps = (long long)batch * (dim / 32), fullm = 148LL * 4;
-  const long long target = 4 * fullm;
-  int nsplit = 1;
-  if (warps < fullm) nsplit = (int)std::min<long long>((target + warps - 1) / warps, kOpMaxSplit);
+  // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY).  Measured on B200 (profiles/r02_op_split_sweep.txt, r02_ncu_opfwd): a
+  // tile costs about the same 3-5 us whether 1 or 3 warps share an SM sub-partition (latency-bound alone, MUFU-bound together),
+  // so time ~ waves x tiles-per-segment x passes: pick the segment count that minimises that, i.e. fills whole waves of the
+  // resident CTA slots.  Segments need not end on the 2048-position chunk boundaries of `x`: a segment that crosses one writes
+  // that chunk's state itself (true h, prefix product = carry-in x local).
+  const long long ctas_base = (long long)batch * G * p.ctiles_per_group;
+  int nsplit = pick_segments(ctas_base, p.ntiles, 148LL * (N >= 16 ? 3 : 4) * 4 / (p.DT / 32), 2.2, kOpMaxSplit);
   if (force_split > 0) nsplit = std::min(force_split, kOpMaxSplit);
   if (ws == nullptr || ws_bytes < scan_op_tma_workspace_bytes(batch, dim, N)) nsplit = 1;
   const int tps = std::max(1, (p.ntiles + nsplit - 1) / nsplit);

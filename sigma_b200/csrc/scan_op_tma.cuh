@@ -118,6 +118,7 @@ int make_tmap_generic(CUtensorMap *map, CUtensorMapDataType dtype, int rank, con
                       const uint64_t *strides_bytes, const uint32_t *box, CUtensorMapSwizzle swz, CUtensorMapL2promotion promo);
 
 cudaError_t prep_kernel_once(const void *fn);   // scan_op_tma.cu
+int pick_segments(long long ctas_base, int ntiles, long long slots, double pass_factor, int max_split);   // scan_op_tma.cu
 
 // global <- shared, 3-D box (per-warp y / gradient rows)
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {

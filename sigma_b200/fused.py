@@ -118,8 +118,9 @@ _W9 = {}   # id(conv.weight) -> (weakref, version, w9): the (9, Cout, Cin) re-or
 
 def conv3x3(x, conv, gelu=False):
     """Dense 3x3 convolution (pad 1) + bias (+ exact GELU) on a channels-last (B, H, W, Cin) tensor through the implicit-GEMM
-    variant of the tcgen05 kernel (sigma_conv3x3_tf32); precision as linear().  Returns (B, H, W, Cout), or None when the
-    convolution is not of that form (caller falls back to cuDNN)."""
+    variant of the tcgen05 kernel (sigma_conv3x3_tf32).  Precision follows torch's switch for CONVOLUTIONS, as the reference's
+    nn.Conv2d does: torch.backends.cudnn.allow_tf32 = True (torch's default) -> one TF32 MMA per k-step; False -> tf32x3.
+    Returns (B, H, W, Cout), or None when the convolution is not of that form (caller falls back to cuDNN)."""
     import weakref
     if conv.kernel_size != (3, 3) or conv.stride != (1, 1) or conv.padding != (1, 1) or conv.dilation != (1, 1) or conv.groups != 1 \
             or conv.in_channels % 4 or conv.out_channels % 4 or not USE_TCGEN05_GEMM:
@@ -135,7 +136,7 @@ def conv3x3(x, conv, gelu=False):
         _W9[key] = ent
     w9 = ent[2]
     y = torch.empty((B, H, W, conv.out_channels), dtype=torch.float32, device=x.device)
-    if precision() == "tf32":
+    if torch.backends.cudnn.allow_tf32:
         hi, lo = w9, None
     else:
         hi, lo = _split_weight(w9)

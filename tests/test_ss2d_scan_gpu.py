@@ -275,7 +275,7 @@ def test_tcgen05_conv3x3_implicit_gemm(B, H, W, Cin, Cout, gelu, mode):
     """sigma_conv3x3_tf32 (3x3 conv as 9 shifted TMA boxes x Cin blocks on the tcgen05 kernel; zero padding = TMA out-of-bounds
     fill; bias + exact GELU in the epilogue) vs torch's conv2d in fp64, ragged image sizes included."""
     from sigma_b200 import fused
-    torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
+    torch.backends.cudnn.allow_tf32 = mode == "tf32"      # convolutions follow torch's cuDNN switch
     tag = f"conv/{B}/{H}/{W}/{Cin}/{Cout}"
     conv = torch.nn.Conv2d(Cin, Cout, 3, 1, 1)
     x = P.randn(S, tag + "/x", (B, H, W, Cin))
