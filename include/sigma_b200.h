@@ -126,6 +126,24 @@ int sigma_ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const floa
                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f1. Backward of the fused scan (training): replaces the autograd of CrossScan (vmamba.py:80-98) + the dt_proj einsum (:199) +
+ * SelectiveScan (selective_scan_bwd_kernel.cuh:68-274) + CrossMerge (:100-121) without materialising the (B,4,D,L) copies.
+ * kind = SIGMA_DIRS_CROSS4 or SIGMA_DIRS_SEQ2; d_state in {4, 16}; D % 64 == 0.  Inputs as the forward plus
+ *   dy      (batch, Lseq, D)      gradient of the MERGED output y = sum_k y_k (CrossMerge is a sum, so every direction sees dy)
+ * Outputs (fp32):
+ *   dxc     (batch, Lseq, D)      sum over directions of du, accumulated by TMA reduce-add (zeroed inside)
+ *   ddelta  (K, batch, Lseq, D)   gradient w.r.t. the PRE-softplus dt_proj output, per direction, at the position it belongs to; the
+ *                                 caller finishes d dt_r = ddelta_k · W_dt[k] and dW_dt[k] = ddelta_k^T · dt_r_k with two GEMMs
+ *   dxdbl   (batch, Lseq, K, Cp)  dB in columns [0, N), dC in [N, 2N) (zeroed inside; dt_r columns left 0 for the caller)
+ *   dA (K·D, N), dDs (K·D), ddtb (K, D)   overwritten
+ *   delta   (K, batch, Lseq, D)   scratch: the recomputed softplus(dt_proj) slabs
+ * ------------------------------------------------------------------------------------------ */
+size_t sigma_ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, int N);
+int sigma_ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                        const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
+                        int H, int W, int D, int N, int R, int Cp, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * Row-wise / stencil pieces of a5-a11 (channels-last, fp32; D % 4 == 0, 16-byte aligned rows).
  * ------------------------------------------------------------------------------------------ */
 /* nn.LayerNorm over the last dim (vmamba.py:1693,724,2173; eps=1e-5): y = (x-mean)/sqrt(var+eps)·w+b */

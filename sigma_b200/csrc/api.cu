@@ -160,6 +160,10 @@ size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N);
 int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
                   const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
                   size_t ws_bytes, int force_split, cudaStream_t stream);
+size_t ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, int N);
+int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                  const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
+                  int H, int W, int D, int N, int R, int Cp, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream);
 int upsample2x_norm_launch(const float *in, const float *gamma, const float *beta, const float *wcls, int ncls, float *out,
                            int B, int Hin, int Win, int C, float eps, cudaStream_t stream);
 int pool_avgmax_partial_launch(const float *x, float *partial, int B, long long L, int C, int nslice, cudaStream_t stream);
@@ -291,6 +295,40 @@ int sigma_ss2d_scan_fwd_split(int kind, const float *xc, const float *xdbl, cons
   if (rc) return rc;
   return ss2d_scan_fwd(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp, workspace, workspace_bytes, nsplit,
                        (cudaStream_t)stream);
+}
+
+size_t sigma_ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, int N) {
+  if (kind != SIGMA_DIRS_CROSS4 && kind != SIGMA_DIRS_SEQ2) return 0;
+  return ss2d_scan_bwd_workspace_bytes(kind, batch, H, W, D, N);
+}
+
+static int ss2d_bwd_entry(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                          const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb,
+                          int batch, int H, int W, int D, int N, int R, int Cp, void *ws, size_t wsb, int nsplit, void *stream) {
+  SIGMA_CHECK_ARG(xc && xdbl && dtw && dtb && A && Ds && dy && delta && dxc && ddelta && dxdbl && dA && dDs && ddtb, "sigma_ss2d_scan_bwd: null pointer");
+  SIGMA_CHECK_ARG(kind == SIGMA_DIRS_CROSS4 || kind == SIGMA_DIRS_SEQ2, "sigma_ss2d_scan_bwd: kind %d unsupported (CROSS4, SEQ2)", kind);
+  SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && D > 0 && D % 64 == 0 && R > 0, "sigma_ss2d_scan_bwd: bad sizes (D=%d must be a multiple of 64)", D);
+  SIGMA_CHECK_ARG(N == 4 || N == 16, "sigma_ss2d_scan_bwd: d_state=%d unsupported (4, 16)", N);
+  SIGMA_CHECK_ARG(Cp == sigma_ss2d_padded_cp(N, R), "sigma_ss2d_scan_bwd: Cp=%d must equal sigma_ss2d_padded_cp(N=%d, R=%d)", Cp, N, R);
+  SIGMA_CHECK_ARG(al16(xc) && al16(xdbl) && al16(dy) && al16(delta) && al16(dxc) && al16(ddelta) && al16(dxdbl), "sigma_ss2d_scan_bwd: pointers must be 16-byte aligned");
+  return ss2d_scan_bwd(kind, xc, xdbl, dtw, dtb, A, Ds, dy, delta, dxc, ddelta, dxdbl, dA, dDs, ddtb, batch, H, W, D, N, R, Cp, ws, wsb, nsplit,
+                       (cudaStream_t)stream);
+}
+
+int sigma_ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                        const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
+                        int H, int W, int D, int N, int R, int Cp, void *workspace, size_t workspace_bytes, void *stream) {
+  return ss2d_bwd_entry(kind, xc, xdbl, dtw, dtb, A, Ds, dy, delta, dxc, ddelta, dxdbl, dA, dDs, ddtb, batch, H, W, D, N, R, Cp, workspace,
+                        workspace_bytes, 0, stream);
+}
+
+// test hook: force the number of L-segments
+int sigma_ss2d_scan_bwd_split(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                              const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb,
+                              int batch, int H, int W, int D, int N, int R, int Cp, void *workspace, size_t workspace_bytes, int nsplit,
+                              void *stream) {
+  return ss2d_bwd_entry(kind, xc, xdbl, dtw, dtb, A, Ds, dy, delta, dxc, ddelta, dxdbl, dA, dDs, ddtb, batch, H, W, D, N, R, Cp, workspace,
+                        workspace_bytes, nsplit, stream);
 }
 
 int sigma_upsample2x_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,

@@ -74,6 +74,11 @@ class composed_path:
         _FORCE_COMPOSED = self.prev
 
 
+def _lib_kinds():
+    from . import _lib
+    return _lib.DIRS_CROSS4, _lib.DIRS_SEQ2
+
+
 def _fused_ok(*tensors):
     """The fused inference path is taken whenever autograd is not recording."""
     if _FORCE_COMPOSED or torch.is_grad_enabled():
@@ -190,8 +195,18 @@ class SS2D(nn.Module):
             return fused.ss2d(self, x, residual=residual)
         xz = self.in_proj(x)
         xi, z = xz.chunk(2, dim=-1)
-        xi = self.act(self.conv2d(xi.permute(0, 3, 1, 2).contiguous()))
-        y = self.forward_core(xi) * F.silu(z)
+        if ops.fused_core_ok(x, self.d_inner, self.d_state):
+            # training through the fused core (f1): conv on the channels_last view, then x_proj + 4-direction scan + CrossMerge as
+            # ONE autograd node over channels-last tensors (no CrossScan / delta / CrossMerge copies in either direction)
+            B, H, W, _ = x.shape
+            xi = self.act(self.conv2d(xi.permute(0, 3, 1, 2)))                       # (B,D,H,W), channels_last memory
+            xc = xi.permute(0, 2, 3, 1).reshape(B, H * W, self.d_inner)
+            y = ops.FusedSS2DCore.apply(xc, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
+                                        _lib_kinds()[0], H, W)
+            y = self.out_norm(y.view(B, H, W, self.d_inner)).to(x.dtype) * F.silu(z)
+        else:
+            xi = self.act(self.conv2d(xi.permute(0, 3, 1, 2).contiguous()))
+            y = self.forward_core(xi) * F.silu(z)
         out = self.dropout(self.out_proj(y))
         return out if residual is None else residual + out
 
@@ -249,7 +264,18 @@ class ConMB_SS2D(nn.Module):
             return fused.conmb_ss2d(self, x_rgb, x_e, residual=residual)
         t_r = self.in_proj(x_rgb).permute(0, 3, 1, 2).contiguous()
         t_e = self.in_proj_modalx(x_e).permute(0, 3, 1, 2).contiguous()
-        y_r, y_e = self.forward_corev2_multimodal(self.act(self.conv2d(t_r)), self.act(self.conv2d_modalx(t_e)))
+        if ops.fused_core_ok(x_rgb, self.d_inner, self.d_state):
+            # training through the fused core (f1), kind SEQ2: [rgb ‖ x] along L, forward + reversed scan, merged
+            B, H, W, _ = x_rgb.shape
+            D, L = self.d_inner, H * W
+            c_r = self.act(self.conv2d(t_r)).permute(0, 2, 3, 1).reshape(B, L, D)
+            c_e = self.act(self.conv2d_modalx(t_e)).permute(0, 2, 3, 1).reshape(B, L, D)
+            ys = ops.FusedSS2DCore.apply(torch.cat([c_r, c_e], dim=1), self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias,
+                                         self.A_logs, self.Ds, _lib_kinds()[1], H, W)                          # (B, 2L, D)
+            y_r = self.out_norm1(ys[:, :L].reshape(B, H, W, D)).to(x_rgb.dtype)
+            y_e = self.out_norm2(ys[:, L:].reshape(B, H, W, D)).to(x_e.dtype)
+        else:
+            y_r, y_e = self.forward_corev2_multimodal(self.act(self.conv2d(t_r)), self.act(self.conv2d_modalx(t_e)))
         g_r = self.fc1(t_r.mean(dim=(2, 3)))          # gates come from the PRE-conv projections (vmamba.py:1276-1279)
         g_e = self.fc2(t_e.mean(dim=(2, 3)))
         y = torch.cat([y_r * g_e[:, None, None, :], y_e * g_r[:, None, None, :]], dim=-1)  # cross-applied (:1280-1281)

@@ -322,3 +322,79 @@ def cross_selective_scan_multimodal_k2(x_rgb, x_e, x_proj_weight=None, x_proj_bi
     y_r = y_r.transpose(1, 2).contiguous().view(B, H, W, D)
     y_e = y_e.transpose(1, 2).contiguous().view(B, H, W, D)
     return out_norm1(y_r).to(x_rgb.dtype), out_norm2(y_e).to(x_e.dtype)
+
+
+# ---- f1: the fused SS2D core under autograd (training) ----
+FUSED_TRAINING = True   # False: the composed path (CrossScan + einsum + op-level scan), kept for A/B and as the general fallback
+
+
+def fused_core_ok(xc, D, N):
+    """The fused training core covers the Sigma configurations: fp32 CUDA activations, d_state in {4, 16}, d_inner % 64 == 0."""
+    return FUSED_TRAINING and xc.is_cuda and N in (4, 16) and D % 64 == 0
+
+
+class FusedSS2DCore(torch.autograd.Function):
+    """cross_selective_scan (vmamba.py:165-226, kind CROSS4) / cross_selective_scan_multimodal_k2 (:369-430, kind SEQ2) without
+    out_norm, on channels-last activations:  xc (B, Lseq, D) -> y (B, Lseq, D) = sum over directions of the scan outputs, each at
+    the position it belongs to (CrossMerge).  Forward = the inference kernels (x_proj GEMM + sigma_ss2d_scan_fwd); backward =
+    sigma_ss2d_scan_bwd (no CrossScan / delta / CrossMerge tensors) + the x_proj / dt_proj weight-gradient GEMMs."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, xc, x_proj_weight, dt_projs_weight, dt_projs_bias, A_logs, Ds, kind, H, W):
+        from . import fused
+        K, _, D = x_proj_weight.shape
+        N, R = A_logs.shape[1], dt_projs_weight.shape[2]
+        Cp = _lib.lib().sigma_ss2d_padded_cp(N, R)
+        xc = xc.contiguous()
+        B, Lseq, _ = xc.shape
+        xw = torch.cat([fused._pack_xproj(x_proj_weight[k], N, R, Cp) for k in range(K)], dim=0).contiguous()      # (K·Cp, D)
+        xdbl = fused.linear(xc.view(B * Lseq, D), xw, kind="x_proj")                                                # (B·Lseq, K·Cp)
+        dtw, dtb = dt_projs_weight.contiguous(), dt_projs_bias.contiguous()
+        A = (-torch.exp(A_logs)).contiguous()
+        Dsc = Ds.contiguous()
+        y = fused.ss2d_scan(kind, xc, xdbl, dtw, dtb, A, Dsc, B, H, W, D, N, R, Cp)                                  # (K, B, Lseq, D)
+        ctx.save_for_backward(xc, xdbl, xw, dtw, dtb, A, Dsc)
+        ctx.meta = (kind, H, W, K, D, N, R, Cp)
+        return y.sum(0)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        from . import fused
+        xc, xdbl, xw, dtw, dtb, A, Ds = ctx.saved_tensors
+        kind, H, W, K, D, N, R, Cp = ctx.meta
+        B, Lseq, _ = xc.shape
+        dy = dy.contiguous().float()
+        dev = xc.device
+        delta = torch.empty((K, B, Lseq, D), dtype=torch.float32, device=dev)
+        ddelta = torch.empty_like(delta)
+        dxc = torch.empty((B, Lseq, D), dtype=torch.float32, device=dev)
+        dxdbl = torch.empty((B * Lseq, K, Cp), dtype=torch.float32, device=dev)
+        dA = torch.empty((K * D, N), dtype=torch.float32, device=dev)
+        dDs = torch.empty(K * D, dtype=torch.float32, device=dev)
+        ddtb = torch.empty((K, D), dtype=torch.float32, device=dev)
+        L_ = _lib.lib()
+        wsb = L_.sigma_ss2d_scan_bwd_workspace_bytes(kind, B, H, W, D, N)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        args = (kind, _ptr(xc), _ptr(xdbl), _ptr(dtw), _ptr(dtb), _ptr(A), _ptr(Ds), _ptr(dy), _ptr(delta), _ptr(dxc), _ptr(ddelta),
+                _ptr(dxdbl), _ptr(dA), _ptr(dDs), _ptr(ddtb), B, H, W, D, N, R, Cp, _ptr(ws), wsb)
+        if fused._FORCE_SPLIT:
+            rc = L_.sigma_ss2d_scan_bwd_split(*args, int(fused._FORCE_SPLIT), _stream())
+        else:
+            rc = L_.sigma_ss2d_scan_bwd(*args, _stream())
+        _lib.check(rc, "sigma_ss2d_scan_bwd")
+        # dt_proj: d dt_r = ddelta_k · W_dt[k]  (into the dt_r columns of dxdbl),  dW_dt[k] = ddelta_k^T · dt_r_k
+        xd3 = xdbl.view(B * Lseq, K, Cp)
+        dW = torch.empty_like(dtw)
+        for k in range(K):
+            ddk = ddelta[k].view(B * Lseq, D)
+            dxdbl[:, k, 2 * N:2 * N + R].copy_(ddk @ dtw[k])
+            dW[k] = ddk.t() @ xd3[:, k, 2 * N:2 * N + R]
+        # x_proj: dxc += dxdbl · xw,  d xw = dxdbl^T · xc
+        d2 = dxdbl.view(B * Lseq, K * Cp)
+        dxc2 = dxc.view(B * Lseq, D)
+        dxc2.addmm_(d2, xw)
+        dxw = (d2.t() @ xc.view(B * Lseq, D)).view(K, Cp, D)
+        dxpw = torch.cat([dxw[:, 2 * N:2 * N + R], dxw[:, 0:N], dxw[:, N:2 * N]], dim=1)          # back to [dt | B | C] rows
+        return dxc, dxpw, dW, ddtb, dA * A, dDs, None, None, None
