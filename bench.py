@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--scan-impl", default="sigma", choices=["sigma", "ref_ext"],
                     help="train mode: ref_ext swaps ONLY the native op for the reference's own CUDA extension (baseline/_ref) under the "
                          "same composition = the reference's training step on this box (the GPU baseline of the training arm)")
+    ap.add_argument("--composed", action="store_true",
+                    help="train mode: CrossScan + einsum + op-level scan kernels (the round-1/2a training path) instead of the fused core")
     ap.add_argument("--ddp-default-buckets", action="store_true",
                     help="train mode: torch DDP's default 25 MB buckets exactly as train.py:103-108 (default here: one aliasing bucket, see train_util.wrap_ddp)")
     ap.add_argument("--train-graph", action="store_true", help="train mode, N = 1: capture the whole step (fwd + bwd + AdamW) in one CUDA graph")
@@ -377,10 +379,13 @@ def run_train(a):
     with contextlib.redirect_stdout(io.StringIO()):
         model = M.EncoderDecoder(cfg_of(a), criterion=torch.nn.CrossEntropyLoss(reduction="mean", ignore_index=255)).to(dev).train()
     if a.scan_impl == "ref_ext":
+        ops.FUSED_TRAINING = False          # the GPU baseline is the reference's COMPOSITION over the reference's extension
         sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
         import selective_scan_cuda_core as ref_ext
         ops.selective_scan_cuda_core_fwd = lambda u, delta, A, Bm, Cm, D=None, bias=None, sp=False, nrows=1, **k: ref_ext.fwd(u, delta, A, Bm, Cm, D, bias, sp, nrows)
         ops.selective_scan_cuda_core_bwd = lambda u, delta, A, Bm, Cm, D, bias, dout, x, sp, nrows=1, **k: ref_ext.bwd(u, delta, A, Bm, Cm, D, bias, dout if dout.stride(-1) == 1 else dout.contiguous(), x, sp, nrows)  # vmamba.py:72-74
+    if a.composed:
+        ops.FUSED_TRAINING = False
     use_graph = a.train_graph and world == 1
     opt = train_util.make_optimizer(model, capturable=use_graph)
     ddp = train_util.wrap_ddp(model, local, single_bucket=not a.ddp_default_buckets)
@@ -478,12 +483,36 @@ def run_train(a):
         rec.append((True, e0, e1, scan_algo_bytes_op(u.shape[0], u.shape[1], u.shape[2], A.shape[1], Bm.shape[1], u.element_size(), True)))
         return out
 
+    # the fused core (f1): sigma_ss2d_scan_fwd / sigma_ss2d_scan_bwd on channels-last tensors, same algorithmic-bytes formula
+    from sigma_b200 import fused
+    ff0, fb0 = fused.ss2d_scan, ops._call_ss2d_bwd
+
+    def ffwd_rec(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = ff0(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp)
+        e1.record()
+        K, L = (4, H * W) if kind == _lib.DIRS_CROSS4 else ((2, 2 * H * W) if kind == _lib.DIRS_SEQ2 else (1, H * W))
+        rec.append((False, e0, e1, scan_algo_bytes_op(batch, K * D, L, N, K, 4, False)))
+        return out
+
+    def fbwd_rec(args):
+        kind, batch, H, W, D, N = args[0], args[15], args[16], args[17], args[18], args[19]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fb0(args)
+        e1.record()
+        K, L = (4, H * W) if kind == _lib.DIRS_CROSS4 else (2, 2 * H * W)
+        rec.append((True, e0, e1, scan_algo_bytes_op(batch, K * D, L, N, K, 4, True)))
+
     ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = fwd_rec, bwd_rec
+    fused.ss2d_scan, ops._call_ss2d_bwd = ffwd_rec, fbwd_rec
     try:
         eager_step(rgb, mx, gt, sync=False)
         torch.cuda.synchronize()
     finally:
         ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = f0, b0
+        fused.ss2d_scan, ops._call_ss2d_bwd = ff0, fb0
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -500,7 +529,8 @@ def run_train(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tot_b, tot_ms = agg[False][0] + agg[True][0], agg[False][1] + agg[True][1]
-    roofline = {"bound": "hbm", "kernel": "scan_op_tma_kernel + scan_op_bwd_tma_kernel (op-level selective scan, forward and backward)"
+    roofline = {"bound": "hbm", "kernel": "fused SS2D core (ss2d_scan_kernel forward; ss2d_state_kernel + ss2d_bwd_kernel backward) for SS2D / ConMB, "
+                                           "op-level scan_op_tma / scan_op_bwd_tma kernels for CroMB"
                 if a.scan_impl == "sigma" else "reference selective_scan_fwd_kernel / selective_scan_bwd_kernel (GPU baseline)",
                 "achieved": round(tot_b / (tot_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(tot_b / (tot_ms * 1e-3) / 1e9 / peak, 4), "traffic": None,
@@ -520,7 +550,7 @@ def run_train(a):
                    "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": (f"DDP x{world} (NCCL all-reduce of {gb / 1e6:.0f} MB fp32 gradients per step, "
                                    + ("default 25 MB buckets" if a.ddp_default_buckets else "one bucket aliasing .grad") + ")") if world > 1 else "single GPU",
-                   "path": "composed (torch autograd over sigma_scan_fwd / sigma_scan_bwd)" if a.scan_impl == "sigma" else
+                   "path": "fused SS2D core under autograd (sigma_ss2d_scan_fwd / sigma_ss2d_scan_bwd) + torch composition around it" if a.scan_impl == "sigma" else
                            "GPU BASELINE: the same composition over the reference's own selective_scan_cuda_core (rebuilt for sm_100a)",
                    "scan_impl": a.scan_impl, "cuda_graph": graph_note, "l2": "256 MiB flush between timed steps",
                    "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},

@@ -59,6 +59,75 @@ static bool force_generic() {
   return e && atoi(e) > 0;
 }
 
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// ---- 16-bit tensors whose rows are not 16-byte aligned (L % 8 != 0, e.g. the 15 x 20 stage) cannot be TMA boxes.  When the
+// fp32 image of the call IS eligible (L % 4 == 0), it is cheaper to widen the operands into scratch, run the TMA-staged fp32
+// kernels and narrow the results than to take the generic kernels (measured: 0.2-0.6x of the reference kernel there). ----
+template <typename T> __device__ __forceinline__ float wide(T v);
+template <> __device__ __forceinline__ float wide<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float wide<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T narrow(float v);
+template <> __device__ __forceinline__ __half narrow<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 narrow<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// src (n0, n1, n2, L) with element strides (s0, s1, s2, 1) -> dst contiguous fp32
+template <typename T>
+__global__ void widen_kernel(const T *__restrict__ src, float *__restrict__ dst, int n1, int n2, int L, long long s0, long long s1,
+                             long long s2, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i % L);
+    long long r = i / L;
+    const int i2 = (int)(r % n2); r /= n2;
+    const int i1 = (int)(r % n1); r /= n1;
+    dst[i] = wide<T>(src[r * s0 + i1 * s1 + i2 * s2 + l]);
+  }
+}
+// src contiguous fp32 (n0, n1, L) -> dst with strides (s0, s1, 1)
+template <typename T>
+__global__ void narrow_kernel(const float *__restrict__ src, T *__restrict__ dst, int n1, int L, long long s0, long long s1, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int l = (int)(i % L);
+    long long r = i / L;
+    const int i1 = (int)(r % n1); r /= n1;
+    dst[r * s0 + i1 * s1 + l] = narrow<T>(src[i]);
+  }
+}
+template <typename T>
+static int widen(const void *src, float *dst, int n0, int n1, int n2, int L, long long s0, long long s1, long long s2, cudaStream_t st) {
+  const long long total = (long long)n0 * n1 * n2 * L;
+  widen_kernel<T><<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>((const T *)src, dst, n1, n2, L, s0, s1, s2, total);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+template <typename T>
+static int narrow_to(const float *src, void *dst, int n0, int n1, int L, long long s0, long long s1, cudaStream_t st) {
+  const long long total = (long long)n0 * n1 * L;
+  narrow_kernel<T><<<(unsigned)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, (T *)dst, n1, L, s0, s1, total);
+  SIGMA_CHECK_LAUNCH();
+  return SIGMA_OK;
+}
+
+static bool widen_shape_ok(int dim, int L, int N, int G, int elem_bytes) {
+  return elem_bytes == 2 && L % 8 != 0 && L % 4 == 0 && (N == 4 || N == 8 || N == 16) && (dim / G) % 32 == 0;
+}
+static size_t widen_fwd_bytes(int batch, int dim, int L, int N, int G) {
+  return 3 * align256((size_t)batch * dim * L * 4) + 2 * align256((size_t)batch * G * N * L * 4);
+}
+static size_t widen_bwd_bytes(int batch, int dim, int L, int N, int G) {
+  return 5 * align256((size_t)batch * dim * L * 4) + 2 * align256((size_t)batch * G * N * L * 4);
+}
+static sigma_scan_strides contiguous_strides(int dim, int L, int N, int G) {
+  sigma_scan_strides st;
+  st.u_batch = st.delta_batch = st.out_batch = (int64_t)dim * L;
+  st.u_dim = st.delta_dim = st.out_dim = L;
+  st.A_dim = N; st.A_dstate = 1;
+  st.B_batch = st.C_batch = (int64_t)G * N * L;
+  st.B_group = st.C_group = (int64_t)N * L;
+  st.B_dstate = st.C_dstate = L;
+  return st;
+}
+
 template <typename T>
 static int scan_fwd_dispatch(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,
                              const float *bias, void *out, float *x, int batch, int dim, int L, int N, int G, int softplus,
@@ -66,6 +135,25 @@ static int scan_fwd_dispatch(const void *u, const void *delta, const float *A, c
   if (!force_generic() && scan_op_tma_eligible<T>(u, delta, B, C, out, dim, L, N, G, s))
     return scan_op_fwd_tma<T>(u, delta, A, B, C, D, bias, out, x, nullptr, batch, dim, L, N, G, softplus, s, ws, ws_bytes,
                               force_split, stream);
+  if constexpr (sizeof(T) == 2) {
+    const size_t core = align256(scan_op_tma_workspace_bytes(batch, dim, N));
+    if (!force_generic() && widen_shape_ok(dim, L, N, G, 2) && ws != nullptr && ws_bytes >= core + widen_fwd_bytes(batch, dim, L, N, G) &&
+        s.A_dstate >= 0) {
+      char *w = (char *)ws + core;
+      const size_t bdl = align256((size_t)batch * dim * L * 4), bgn = align256((size_t)batch * G * N * L * 4);
+      float *u32 = (float *)w, *d32 = (float *)(w + bdl), *o32 = (float *)(w + 2 * bdl), *B32 = (float *)(w + 3 * bdl), *C32 = (float *)(w + 3 * bdl + bgn);
+      int rc;
+      if ((rc = widen<T>(u, u32, batch, dim, 1, L, s.u_batch, s.u_dim, 0, stream))) return rc;
+      if ((rc = widen<T>(delta, d32, batch, dim, 1, L, s.delta_batch, s.delta_dim, 0, stream))) return rc;
+      if ((rc = widen<T>(B, B32, batch, G, N, L, s.B_batch, s.B_group, s.B_dstate, stream))) return rc;
+      if ((rc = widen<T>(C, C32, batch, G, N, L, s.C_batch, s.C_group, s.C_dstate, stream))) return rc;
+      sigma_scan_strides cs = contiguous_strides(dim, L, N, G);
+      cs.A_dim = s.A_dim; cs.A_dstate = s.A_dstate;
+      if ((rc = scan_op_fwd_tma<float>(u32, d32, A, B32, C32, D, bias, o32, x, nullptr, batch, dim, L, N, G, softplus, cs, ws, core, force_split,
+                                       stream))) return rc;
+      return narrow_to<T>(o32, out, batch, dim, L, s.out_batch, s.out_dim, stream);
+    }
+  }
   return scan_op_fwd_generic<T>(u, delta, A, B, C, D, bias, out, x, nullptr, batch, dim, L, N, G, softplus, s, ws, ws_bytes,
                                 force_split, stream);
 }
@@ -75,22 +163,33 @@ static int scan_bwd_dispatch(const void *u, const void *delta, const float *A, c
                              const float *bias, const void *dout, void *du, void *ddelta, float *dA, float *dB, float *dC,
                              float *dD, float *dbias, int batch, int dim, int L, int N, int G, int softplus, void *ws,
                              size_t ws_bytes, int force_split, cudaStream_t stream) {
-  sigma_scan_strides st;   // contiguous
-  st.u_batch = st.delta_batch = st.out_batch = (int64_t)dim * L;
-  st.u_dim = st.delta_dim = st.out_dim = L;
-  st.A_dim = N; st.A_dstate = 1;
-  st.B_batch = st.C_batch = (int64_t)G * N * L;
-  st.B_group = st.C_group = (int64_t)N * L;
-  st.B_dstate = st.C_dstate = L;
+  const sigma_scan_strides st = contiguous_strides(dim, L, N, G);
   const bool al = (((uintptr_t)dout | (uintptr_t)du | (uintptr_t)ddelta | (uintptr_t)dB | (uintptr_t)dC) & 15) == 0;
   if (!force_generic() && al && scan_op_tma_eligible<T>(u, delta, B, C, du, dim, L, N, G, st))
     return scan_op_bwd_tma<T>(u, delta, A, B, C, D, bias, dout, du, ddelta, dA, dB, dC, dD, dbias, batch, dim, L, N, G, softplus,
                               ws, ws_bytes, force_split, stream);
+  if constexpr (sizeof(T) == 2) {
+    const size_t core = align256(scan_op_bwd_tma_workspace_bytes(batch, dim, L, N, 4));
+    if (!force_generic() && widen_shape_ok(dim, L, N, G, 2) && ws_bytes >= core + widen_bwd_bytes(batch, dim, L, N, G)) {
+      char *w = (char *)ws + core;
+      const size_t bdl = align256((size_t)batch * dim * L * 4), bgn = align256((size_t)batch * G * N * L * 4);
+      float *u32 = (float *)w, *d32 = (float *)(w + bdl), *g32 = (float *)(w + 2 * bdl), *du32 = (float *)(w + 3 * bdl), *dd32 = (float *)(w + 4 * bdl);
+      float *B32 = (float *)(w + 5 * bdl), *C32 = (float *)(w + 5 * bdl + bgn);
+      int rc;
+      if ((rc = widen<T>(u, u32, batch, dim, 1, L, st.u_batch, st.u_dim, 0, stream))) return rc;
+      if ((rc = widen<T>(delta, d32, batch, dim, 1, L, st.u_batch, st.u_dim, 0, stream))) return rc;
+      if ((rc = widen<T>(dout, g32, batch, dim, 1, L, st.u_batch, st.u_dim, 0, stream))) return rc;
+      if ((rc = widen<T>(B, B32, batch, G, N, L, st.B_batch, st.B_group, st.B_dstate, stream))) return rc;
+      if ((rc = widen<T>(C, C32, batch, G, N, L, st.C_batch, st.C_group, st.C_dstate, stream))) return rc;
+      if ((rc = scan_op_bwd_tma<float>(u32, d32, A, B32, C32, D, bias, g32, du32, dd32, dA, dB, dC, dD, dbias, batch, dim, L, N, G, softplus, ws,
+                                       core, force_split, stream))) return rc;
+      if ((rc = narrow_to<T>(du32, du, batch, dim, L, st.u_batch, st.u_dim, stream))) return rc;
+      return narrow_to<T>(dd32, ddelta, batch, dim, L, st.u_batch, st.u_dim, stream);
+    }
+  }
   return scan_op_bwd_generic<T>(u, delta, A, B, C, D, bias, dout, du, ddelta, dA, dB, dC, dD, dbias, batch, dim, L, N, G,
                                 softplus, ws, ws_bytes, stream);
 }
-
-static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace sigma
 
@@ -104,8 +203,11 @@ const char *sigma_last_error(void) { return g_err; }
 uint64_t sigma_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 size_t sigma_scan_fwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype) {
-  (void)seqlen; (void)ngroups; (void)dtype;   // every element type is read natively: only the L-segment carries need scratch
-  return align256(std::max(scan_op_workspace_bytes(batch, dim, dstate), scan_op_tma_workspace_bytes(batch, dim, dstate)));
+  // every element type is read natively: only the L-segment carries need scratch — plus, for 16-bit calls whose rows are not
+  // 16-byte aligned but whose fp32 image is TMA-eligible, the widened operands
+  size_t w = align256(std::max(scan_op_workspace_bytes(batch, dim, dstate), scan_op_tma_workspace_bytes(batch, dim, dstate)));
+  if (dtype != SIGMA_F32 && widen_shape_ok(dim, seqlen, dstate, ngroups, 2)) w += widen_fwd_bytes(batch, dim, seqlen, dstate, ngroups);
+  return w;
 }
 
 int sigma_scan_fwd(const void *u, const void *delta, const float *A, const void *B, const void *C,
@@ -373,10 +475,11 @@ int sigma_scale_add_fwd(const float *a, const float *sa, const float *b, const f
 }
 
 size_t sigma_scan_bwd_workspace_bytes(int batch, int dim, int seqlen, int dstate, int ngroups, int dtype) {
-  (void)ngroups;
   const int eb = dtype == SIGMA_F32 ? 4 : 2;
-  return align256(std::max(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate, eb),
-                           scan_op_bwd_tma_workspace_bytes(batch, dim, seqlen, std::min(dstate, 16), eb)));
+  size_t w = align256(std::max(scan_op_bwd_workspace_bytes(batch, dim, seqlen, dstate, eb),
+                               scan_op_bwd_tma_workspace_bytes(batch, dim, seqlen, std::min(dstate, 16), eb)));
+  if (dtype != SIGMA_F32 && widen_shape_ok(dim, seqlen, dstate, ngroups, 2)) w += widen_bwd_bytes(batch, dim, seqlen, dstate, ngroups);
+  return w;
 }
 
 static int scan_bwd_entry(const void *u, const void *delta, const float *A, const void *B, const void *C, const float *D,

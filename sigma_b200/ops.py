@@ -333,6 +333,17 @@ def fused_core_ok(xc, D, N):
     return FUSED_TRAINING and xc.is_cuda and N in (4, 16) and D % 64 == 0
 
 
+def _call_ss2d_bwd(args):
+    """The native call of the fused backward (a module-level function so that bench.py can bracket it with events)."""
+    from . import fused
+    L_ = _lib.lib()
+    if fused._FORCE_SPLIT:
+        rc = L_.sigma_ss2d_scan_bwd_split(*args, int(fused._FORCE_SPLIT), _stream())
+    else:
+        rc = L_.sigma_ss2d_scan_bwd(*args, _stream())
+    _lib.check(rc, "sigma_ss2d_scan_bwd")
+
+
 class FusedSS2DCore(torch.autograd.Function):
     """cross_selective_scan (vmamba.py:165-226, kind CROSS4) / cross_selective_scan_multimodal_k2 (:369-430, kind SEQ2) without
     out_norm, on channels-last activations:  xc (B, Lseq, D) -> y (B, Lseq, D) = sum over directions of the scan outputs, each at
@@ -379,11 +390,7 @@ class FusedSS2DCore(torch.autograd.Function):
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         args = (kind, _ptr(xc), _ptr(xdbl), _ptr(dtw), _ptr(dtb), _ptr(A), _ptr(Ds), _ptr(dy), _ptr(delta), _ptr(dxc), _ptr(ddelta),
                 _ptr(dxdbl), _ptr(dA), _ptr(dDs), _ptr(ddtb), B, H, W, D, N, R, Cp, _ptr(ws), wsb)
-        if fused._FORCE_SPLIT:
-            rc = L_.sigma_ss2d_scan_bwd_split(*args, int(fused._FORCE_SPLIT), _stream())
-        else:
-            rc = L_.sigma_ss2d_scan_bwd(*args, _stream())
-        _lib.check(rc, "sigma_ss2d_scan_bwd")
+        _call_ss2d_bwd(args)
         # dt_proj: d dt_r = ddelta_k · W_dt[k]  (into the dt_r columns of dxdbl),  dW_dt[k] = ddelta_k^T · dt_r_k
         xd3 = xdbl.view(B * Lseq, K, Cp)
         dW = torch.empty_like(dtw)

@@ -148,3 +148,29 @@ def test_bwd_tma_path(b, d, n, L, G, dn):
         check(ops.selective_scan_cuda_core_bwd(*args), "generic")
     finally:
         del os.environ["SIGMA_OP_GENERIC"]
+
+
+@pytest.mark.parametrize("dn", ["bf16", "f16"])
+def test_unaligned_16bit_rows_take_the_widened_tma_route(dn):
+    """16-bit tensors with L % 8 == 4 (the 15 x 20 stage: 600-byte rows) cannot be TMA boxes; their fp32 image can: operands are
+    widened into scratch, the TMA-staged fp32 kernels run, results are narrowed.  Forward and all gradients vs the C oracle."""
+    from sigma_b200 import ops
+    dt = {"bf16": torch.bfloat16, "f16": torch.float16}[dn]
+    b, d, n, L, G = 2, 128, 16, 300, 4
+    u, dl, A, Bm, Cm, D, bias = P.scan_inputs(SEED + 13, b, d, n, L, G)
+    dout = P.randn(SEED + 13, "widen/do", (b, d, L))
+    q = lambda t: t.to(dt)
+    f = lambda t: q(t).float().numpy()
+    ref = scan_oracle.scan_fwd(f(u), f(dl), A.numpy(), f(Bm), f(Cm), D.numpy(), bias.numpy(), True)
+    out, _ = ops.selective_scan_cuda_core_fwd(q(u).cuda(), q(dl).cuda(), A.cuda(), q(Bm).cuda(), q(Cm).cuda(), D.cuda(), bias.cuda(), True, 1)
+    rt, at = (3e-2, 5e-2) if dn == "bf16" else (3e-3, 5e-3)
+    assert out.dtype == dt
+    assert_close(out, ref, rt, at, f"widened fwd {dn}")
+    names = ["du", "ddelta", "dA", "dB", "dC", "dD", "dbias"]
+    rb = scan_oracle.scan_bwd(f(u), f(dl), A.numpy(), f(Bm), f(Cm), D.numpy(), bias.numpy(), f(dout), True)
+    res = ops.selective_scan_cuda_core_bwd(q(u).cuda(), q(dl).cuda(), A.cuda(), q(Bm).cuda(), q(Cm).cuda(), D.cuda(), bias.cuda(),
+                                           q(dout).cuda(), None, True, 1)
+    assert res[0].dtype == dt
+    for name, got, r in zip(names, res, rb):
+        rt2, at2 = (3e-2, 5e-2) if dn == "bf16" else (6e-3, 1e-2)
+        assert_close(got, r, rt2, at2 * max(1.0, float(np.abs(r).max()) / 50.0), f"widened bwd {name} {dn}")
