@@ -117,10 +117,13 @@ __device__ __forceinline__ FbWalk fb_walk(const Ss2dBwdParams &p) {
 template <int N, int MODE>
 __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constant__ Ss2dBwdParams p) {
   constexpr int LPC = FbCfg<N>::LPC, NS = FbCfg<N>::NS, CPW = FbCfg<N>::CPW, NT = FB_DT * LPC;
+  // delta' does not depend on the state: the pass that sees a position FIRST (MODE_SERIAL, or MODE_SUMMARY when the walk is
+  // cut into L-segments) computes it and stores the slab tile; MODE_APPLY reads it back instead of repeating the dot product
+  constexpr bool COMPUTE = MODE != MODE_APPLY, STATES = MODE != MODE_SUMMARY;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float *smem = reinterpret_cast<float *>(smem_raw);
   const int NST = p.nst, Cp = p.Cp, R = p.R;
-  const int xc_fl = FB_LT * FB_DT, dbl_fl = FB_LT * Cp, stage_fl = xc_fl + dbl_fl;
+  const int xc_fl = FB_LT * FB_DT, dbl_fl = FB_LT * Cp, stage_fl = xc_fl + dbl_fl + (COMPUTE ? 0 : xc_fl);   // xc | dbl | [delta']
   float *stage_all = smem + NST * stage_fl;                // per-warp delta staging [16][CPW] (TMA store source: keep it aligned)
   float *sW = stage_all + (NT / 32) * FB_LT * CPW;         // W_dt rows of this CTA's channels, pitch R + 1
   uint64_t *full = reinterpret_cast<uint64_t *>(sW + ((FB_DT * (R + 1) + 1) & ~1));
@@ -134,9 +137,11 @@ __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constan
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
     fence_mbar_init();
   }
-  for (int i = tid; i < FB_DT * R; i += NT) {
-    const int cc = i / R, r = i - cc * R;
-    sW[cc * (R + 1) + r] = p.dtw[((long long)w.k * p.D + w.d0 + cc) * R + r];
+  if (COMPUTE) {
+    for (int i = tid; i < FB_DT * R; i += NT) {
+      const int cc = i / R, r = i - cc * R;
+      sW[cc * (R + 1) + r] = p.dtw[((long long)w.k * p.D + w.d0 + cc) * R + r];
+    }
   }
   __syncthreads();
   if (w.t0 >= w.t1) return;
@@ -148,6 +153,7 @@ __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constan
     mbar_arrive_expect_tx(&full[st], tx);
     tma_load_4d(dst, &p.m_xc[w.k], &full[st], w.d0, i0, o, w.b);
     tma_load_4d(dst + xc_fl, &p.m_dbl[w.k], &full[st], 0, i0, o, w.b);
+    if (!COMPUTE) tma_load_4d(dst + xc_fl + dbl_fl, &p.m_dl[w.k], &full[st], w.d0, i0, o, w.k * p.batch + w.b);
   };
   if (tid == 0) for (int tau = w.t0; tau < min(w.t1, w.t0 + NST); ++tau) request_tile(tau, tau - w.t0);
 
@@ -170,8 +176,8 @@ __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constan
     int o, i0, npos;
     w.tile(tau, o, i0, npos);
     mbar_spin(&full[st], (uint32_t)ph);
-    const float *sXC = smem + st * stage_fl, *sDB = sXC + xc_fl;
-    if (MODE != MODE_SUMMARY) {   // state at the start of the tile (walk order)
+    const float *sXC = smem + st * stage_fl, *sDB = sXC + xc_fl, *sDL = sDB + dbl_fl;
+    if (STATES) {   // state at the start of the tile (walk order)
       float4 *hp = reinterpret_cast<float4 *>(p.hs + (((((long long)w.k * p.batch + w.b) * p.max_tiles + tau) * p.D + d) * N + n0));
 #pragma unroll
       for (int q = 0; q < NS / 4; ++q) hp[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
@@ -180,9 +186,19 @@ __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constan
     for (int s = 0; s < npos; ++s) {
       const int r = w.rev ? npos - 1 - s : s;
       const float *row = sDB + r * Cp;
-      float acc = bias;
-      for (int q = 0; q < R; ++q) acc = fmaf(wrow[q], row[2 * N + q], acc);
-      const float dl = softplus20(acc);
+      float dl;
+      if (COMPUTE) {
+        dl = 0.f;
+        if (half == 0) {           // one lane per channel evaluates dt_proj + softplus; its partner lane (d_state 16) receives it
+          float acc = bias;
+          for (int q = 0; q < R; ++q) acc = fmaf(wrow[q], row[2 * N + q], acc);
+          dl = softplus20(acc);
+          stg[r * CPW + cl] = dl;
+        }
+        if (LPC == 2) dl = __shfl_sync(0xffffffffu, dl, cl);
+      } else {
+        dl = sDL[r * FB_DT + c];
+      }
       const float du = dl * sXC[r * FB_DT + c];
 #pragma unroll
       for (int q = 0; q < NS / 4; ++q) {
@@ -193,9 +209,8 @@ __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constan
         h[4 * q + 3] = fmaf(ex2(dl * a2[4 * q + 3]), h[4 * q + 3], du * bv.w);
       }
       sumdl += dl;
-      if (MODE != MODE_SUMMARY && half == 0) stg[r * CPW + cl] = dl;
     }
-    if (MODE != MODE_SUMMARY) {
+    if (COMPUTE) {
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(128, 3) ss2d_state_kernel(const __grid_constan
     }
     if (++st == NST) { st = 0; ph ^= 1; }
   }
-  if (MODE != MODE_SUMMARY && lane == 0) tma_store_wait_all<0>();
+  if (COMPUTE && lane == 0) tma_store_wait_all<0>();
   if (MODE == MODE_SUMMARY) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
@@ -534,7 +549,7 @@ int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw
     constexpr int LPC = FbCfg<NN>::LPC, NS = FbCfg<NN>::NS, CPWc = FbCfg<NN>::CPW, NT = FB_DT * LPC;
     dim3 grid(D / FB_DT, K * pm.nsplit, batch), block(NT);
     const long long nrows = (long long)batch * K * D, tot = nrows * NN;
-    const size_t st_smem = ((size_t)pm.nst * (FB_LT * FB_DT + FB_LT * Cp) + FB_DT * (R + 1) + 2 + (NT / 32) * FB_LT * CPWc) * sizeof(float) + 256;
+    const size_t st_smem = ((size_t)pm.nst * (2 * FB_LT * FB_DT + FB_LT * Cp) + FB_DT * (R + 1) + 2 + (NT / 32) * FB_LT * CPWc) * sizeof(float) + 256;
     const size_t sm_smem = ((size_t)pm.nst * (2 * FB_LT * FB_DT + FB_LT * Cp)) * sizeof(float) + 256;
     const size_t mn_smem = ((size_t)pm.nst * (3 * FB_LT * FB_DT + FB_LT * Cp) + (NT / 32) * 2 * FB_LT * CPWc + (size_t)FB_LT * NS * NT) * sizeof(float) + 256;
     auto run = [&](auto kern, const Ss2dBwdParams &pp, size_t smem) -> int {
