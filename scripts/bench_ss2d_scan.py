@@ -18,6 +18,9 @@ SHAPES = [
     ("enc2", "cross4", 2, 30, 40, 768, 16, 24), ("enc3", "cross4", 2, 15, 20, 1536, 16, 48),
     ("dec0", "cross4", 1, 120, 160, 192, 4, 6), ("dec1", "cross4", 1, 60, 80, 384, 4, 12), ("dec2", "cross4", 1, 30, 40, 768, 4, 24),
     ("conmb0", "seq2", 1, 120, 160, 192, 4, 6), ("cromb0", "cross", 2, 120, 160, 192, 4, 6),
+    ("conmb1", "seq2", 1, 60, 80, 384, 4, 12), ("cromb1", "cross", 2, 60, 80, 384, 4, 12),
+    ("conmb2", "seq2", 1, 30, 40, 768, 4, 24), ("cromb2", "cross", 2, 30, 40, 768, 4, 24),
+    ("conmb3", "seq2", 1, 15, 20, 1536, 4, 48), ("cromb3", "cross", 2, 15, 20, 1536, 4, 48),
 ]
 KID = {"cross4": _lib.DIRS_CROSS4, "seq2": _lib.DIRS_SEQ2, "cross": _lib.DIRS_CROSS}
 

@@ -165,7 +165,11 @@ __global__ void __launch_bounds__(128, OpCfg<NP>::CTAS) scan_op_tma_kernel(const
       load_group<T, G>(sDl, tid, 0, raw);
       load_group<T, G>(sU, tid, 0, u);
 #pragma unroll
-      for (int i = 0; i < G; ++i) { const float r = raw[i] + bias; dl[i] = sp ? softplus20(r) : r; }
+      for (int i = 0; i < G; i += 2) {   // softplus of two positions per FFMA2 (G is even)
+        const float r0 = raw[i] + bias, r1 = raw[i + 1] + bias;
+        const f2 s2 = sp ? softplus20x2(r0, r1) : f2{r0, r1};
+        dl[i] = s2.x; dl[i + 1] = s2.y;
+      }
     }
 #pragma unroll 1
     for (int gi = 0; gi < ng; ++gi) {
@@ -182,7 +186,11 @@ __global__ void __launch_bounds__(128, OpCfg<NP>::CTAS) scan_op_tma_kernel(const
         load_group<T, G>(sDl, tid, gn, raw);
         load_group<T, G>(sU, tid, gn, un);
 #pragma unroll
-        for (int i = 0; i < G; ++i) { const float r = raw[i] + bias; dln[i] = sp ? softplus20(r) : r; }
+        for (int i = 0; i < G; i += 2) {
+          const float r0 = raw[i] + bias, r1 = raw[i + 1] + bias;
+          const f2 s2 = sp ? softplus20x2(r0, r1) : f2{r0, r1};
+          dln[i] = s2.x; dln[i + 1] = s2.y;
+        }
       }
       const int cnt = npos - gi * G;      // valid positions of this group (>= 1)
       float yv[G];

@@ -37,8 +37,12 @@ struct Ss2dCfg {
   static constexpr int LT = N >= 16 ? 16 : 32;    // scan positions per tile (multiple of G; measured: 16 loses at N=4)
   static constexpr int MAX_NST = 8;               // TMA ring depth is chosen on the host (Ss2dParams::nst), up to this
   static constexpr int MAXW = 4;                  // warps per CTA
-  static constexpr int CTAS = 3;                  // resident CTAs per SM the register budget is set for (168 regs)
+  static constexpr int CTAS = 3;                  // default resident 128-thread CTAs per SM the register budget is set for (168 regs)
 };
+// The kernel is built for two register budgets (`__launch_bounds__(128, CTAS)`): 3 -> 168 registers (12 warps per SM)
+// and, for d_state 16, 4 -> 128 registers (16 warps; no spills inside the position loop).  The host picks per
+// (d_state, padded dt_rank) from measurements (ss2d_scan_host.cu: ss2d_pick_ctas).
+__host__ __device__ constexpr int ss2d_reg_cap(int ctas) { return (65536 / (ctas * 128)) / 8 * 8; }
 
 struct alignas(64) Ss2dParams {
   CUtensorMap m_xc[4], m_dbl[4];
@@ -64,6 +68,8 @@ __host__ __device__ inline size_t ss2d_smem_bytes(int LT, int DT, int NST, int C
   const size_t stage = (size_t)LT * DT + (size_t)LT * Cp * (cross ? 2 : 1);
   return NST * stage * sizeof(float) + 128 /*barriers + counters*/;
 }
+
+static __device__ float g_ss2d_sink[32];   // y of threads whose channel is >= D goes here (never read)
 
 template <int N, int CPT, int RP>
 struct Ss2dThread {
@@ -122,20 +128,30 @@ __device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, 
       const f2 s0 = unpack2(acc0[c]);
       float x = s0.x + s0.y;
       if (TWO) { const f2 s1 = unpack2(acc1[c]); x += s1.x + s1.y; }
-      dl[c][e] = softplus20(x);
+      dl[c][e] = x;                                   // pre-activation; softplus below, two positions per FFMA2
       u[c][e] = xrow[e * DT + c * cstride];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+#pragma unroll
+    for (int e = 0; e < G; e += 2) {
+      const f2 sp = softplus20x2(dl[c][e], dl[c][e + 1]);
+      dl[c][e] = sp.x; dl[c][e + 1] = sp.y;
     }
   }
 }
 
 // recurrence over `cnt` (<= G) positions of one group, in walk order (REV: descending tile rows).  `rb` = first
-// x_dbl row of the group (B part), `rc` = same row in the tile C is read from, `yp` = y of the group's first
-// position (this thread's first channel), `ystride` = y elements between consecutive positions.
+// x_dbl row of the group (B part), `rc` = same row in the tile C is read from, `yq` = y of the group's first WALKED
+// position (this thread's channel), `ystep` = y elements from one walked position to the next (negative when REV):
+// the address is a running pointer (one IMAD.WIDE per position) and the store is unconditional — a thread whose
+// channel lies beyond D walks a one-element sink instead (kernel prologue), so there is no branch around the store.
 // Per position B and C are read ONCE (2·N/4 broadcast LDS.128) and reused by the CPT channels of the thread;
 // per channel and state pair: FMUL2 (exp arguments), 2 x MUFU.EX2, FMUL2 (delta·u·B), FFMA2 (h), FFMA2 (C·h).
 template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL>
-__device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *rb, const float *rc, float *yp,
-                                           long long ystride, int ycstride, const float (&dl)[CPT][G],
+__device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *rb, const float *rc, float *yq,
+                                           int ystep, int ycstride, const float (&dl)[CPT][G],
                                            const float (&u)[CPT][G], int cnt) {
   constexpr int Cp = 2 * N + RP;
   constexpr int NCH = N >= 8 ? 2 : 1;   // independent C·h accumulator chains per channel
@@ -177,12 +193,13 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
           float y = yacc[c][0].x + yacc[c][0].y;
           if (NCH == 2) y += yacc[c][1].x + yacc[c][1].y;
           if (SIGMA_ABL(t.ablate, 1)) t.sumdl[c] += y;
-          else if (t.ok[c]) yp[(long long)i * ystride + c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
+          else yq[c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
         } else {
           t.sumdl[c] += dl[c][i];
         }
       }
     }
+    if (WITH_Y) yq += ystep;
   }
 }
 
@@ -194,6 +211,7 @@ struct Ss2dWalk {
   uint32_t *done;
   float *ybase;
   long long istride, ostride;
+  int ystep;   // y elements from one walked position to the next (sign follows the walk direction; 0 on the sink)
   int stage_fl, xc_fl, dbl_fl, DT, nwarps, lane, ch;
   int t0, t1, TPO, ntiles, I, nst;
   bool cross, rev;
@@ -210,7 +228,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
 
   // ring slot / phase and (outer index, inner tile) of the tile being opened advance incrementally: no division
   // or modulo per tile.  Tiles are walked in ascending tau; reversed directions map tau -> ntiles-1-tau.
-  struct Tile { const float *sXC, *sDB, *sDC; float *yrow; int npos, ng; };
+  struct Tile { const float *sXC, *sDB, *sDC; float *ystart; int npos, ng; };   // ystart: y of the tile's first WALKED group start
   int ost = 0, oph = 0;                                  // slot and phase parity of the next tile to open
   int tm0 = w.rev ? w.ntiles - 1 - w.t0 : w.t0;          // memory-order tile index of tile t0
   int oo = tm0 / w.TPO, oti = tm0 - oo * w.TPO;          // its (outer index, inner tile)
@@ -223,7 +241,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
     const int i0 = oti * LT;
     T.npos = min(LT, w.I - i0);
     T.ng = (T.npos + G - 1) / G;
-    T.yrow = w.ybase + (long long)oo * w.ostride + (long long)i0 * w.istride;
+    T.ystart = w.ybase + (long long)oo * w.ostride + (long long)(i0 + (REV ? T.ng * G - 1 : 0)) * w.istride;
     if (++ost == w.nst) { ost = 0; oph ^= 1; }
     if (w.rev) { if (--oti < 0) { oti = w.TPO - 1; --oo; } }
     else       { if (++oti == w.TPO) { oti = 0; ++oo; } }
@@ -237,6 +255,8 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
   group_prologue<N, CPT, RP, G>(t, cur.sXC + j * G * w.DT + w.ch, cur.sDB + j * G * Cp + 2 * N, w.DT, dl, u);
 
   int rst = 0;                    // ring slot of the tile being processed
+  const int gstep = G * w.ystep;  // y elements from one group's first walked position to the next group's
+  float *yp = cur.ystart;         // running y pointer: first walked position of the current group
   for (int tau = w.t0; tau < w.t1; ++tau) {
     Tile nxt = cur;
     int jn = j;
@@ -261,7 +281,6 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
       const int cnt = cur.npos - j * G;
       const float *rb = cur.sDB + j * G * Cp;
       const float *rc = cur.sDC + j * G * Cp + N;
-      float *yp = cur.yrow + (long long)(j * G) * w.istride;
       // prologue(next) and body(current) are independent; keeping them in ONE basic block lets ptxas interleave
       // the prologue's FMA/LG2 work with the body's exponentials (it does not schedule across the cnt branch)
       if (cnt >= G) {
@@ -272,16 +291,17 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
 #pragma unroll
             for (int i = 0; i < G; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
         }
-        group_body<N, CPT, RP, G, WITH_Y, REV, true>(t, rb, rc, yp, w.istride, ycs, dl, u, G);
+        group_body<N, CPT, RP, G, WITH_Y, REV, true>(t, rb, rc, yp, w.ystep, ycs, dl, u, G);
       } else {
         group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
-        group_body<N, CPT, RP, G, WITH_Y, REV, false>(t, rb, rc, yp, w.istride, ycs, dl, u, cnt);
+        group_body<N, CPT, RP, G, WITH_Y, REV, false>(t, rb, rc, yp, w.ystep, ycs, dl, u, cnt);
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
 #pragma unroll
         for (int i = 0; i < G; ++i) { dl[c][i] = dln[c][i]; u[c][i] = un[c][i]; }
       j = jn;
+      yp += gstep;
     }
     // this warp is done with the ring slot; the last of the CTA's warps to get here refills it
     __syncwarp();
@@ -291,11 +311,12 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
     }
     if (++rst == w.nst) rst = 0;
     cur = nxt;
+    yp = cur.ystart;
   }
 }
 
-template <int N, int CPT, int RP, int MODE>
-__global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+template <int N, int CPT, int RP, int MODE, int CTAS>
+__global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   constexpr int LT = Ss2dCfg<N>::LT;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
   const int NST = p.nst;
@@ -387,8 +408,15 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
 
   Ss2dWalk<N, CPT, RP> w;
   w.stages = stages; w.full = full; w.done = done;
-  w.ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + min(d0 + tid, p.D - 1);
-  w.istride = p.istride[k]; w.ostride = p.ostride[k];
+  static_assert(CPT == 1, "the sink redirection below assumes one channel per thread");
+  if (t.ok[0]) {
+    w.ybase = p.y + (((long long)k * p.batch + b) * p.Lseq) * p.D + d0 + tid;
+    w.istride = p.istride[k]; w.ostride = p.ostride[k];
+  } else {                       // channel beyond D (ragged last channel tile): every y address collapses onto the sink
+    w.ybase = &g_ss2d_sink[tid & 31];
+    w.istride = 0; w.ostride = 0;
+  }
+  w.ystep = (int)(rev ? -w.istride : w.istride);
   w.stage_fl = stage_fl; w.xc_fl = xc_fl; w.dbl_fl = dbl_fl; w.DT = DT;
   w.nwarps = NTC >> 5; w.lane = tid & 31; w.ch = tid;
   w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I; w.nst = NST;
@@ -414,6 +442,6 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, Ss2dCfg<N>::CTAS) ss2d_
 // host-side launcher for one (N, CPT, RP) instantiation; defined per RP in ss2d_scan_rp*.cu.
 // `nthreads` = threads per CTA (each owning CPT channels).
 template <int N, int CPT, int RP>
-int ss2d_launch(const Ss2dParams &p, int nthreads, cudaStream_t stream);
+int ss2d_launch(const Ss2dParams &p, int nthreads, int ctas, cudaStream_t stream);
 
 }  // namespace sigma

@@ -58,16 +58,16 @@ static int pad_rp(int R) {
 }
 
 template <int N, int CPT>
-static int dispatch_rp(const Ss2dParams &p, int nthreads, cudaStream_t s) {
+static int dispatch_rp(const Ss2dParams &p, int nthreads, int ctas, cudaStream_t s) {
   switch (pad_rp(p.R)) {
-    case 4: return ss2d_launch<N, CPT, 4>(p, nthreads, s);
-    case 8: return ss2d_launch<N, CPT, 8>(p, nthreads, s);
-    case 12: return ss2d_launch<N, CPT, 12>(p, nthreads, s);
-    case 16: return ss2d_launch<N, CPT, 16>(p, nthreads, s);
-    case 24: return ss2d_launch<N, CPT, 24>(p, nthreads, s);
-    case 32: return ss2d_launch<N, CPT, 32>(p, nthreads, s);
-    case 48: return ss2d_launch<N, CPT, 48>(p, nthreads, s);
-    case 64: return ss2d_launch<N, CPT, 64>(p, nthreads, s);
+    case 4: return ss2d_launch<N, CPT, 4>(p, nthreads, ctas, s);
+    case 8: return ss2d_launch<N, CPT, 8>(p, nthreads, ctas, s);
+    case 12: return ss2d_launch<N, CPT, 12>(p, nthreads, ctas, s);
+    case 16: return ss2d_launch<N, CPT, 16>(p, nthreads, ctas, s);
+    case 24: return ss2d_launch<N, CPT, 24>(p, nthreads, ctas, s);
+    case 32: return ss2d_launch<N, CPT, 32>(p, nthreads, ctas, s);
+    case 48: return ss2d_launch<N, CPT, 48>(p, nthreads, ctas, s);
+    case 64: return ss2d_launch<N, CPT, 64>(p, nthreads, ctas, s);
   }
   set_error("sigma_ss2d_scan_fwd: dt_rank %d > 64 unsupported", p.R);
   return SIGMA_EUNSUPPORTED;
@@ -87,6 +87,14 @@ static int pick_warps(int D, int cpt, int maxw) {
 }
 
 constexpr int kMaxSplit = 32;
+
+// Which register budget to run (`CTAS` of ss2d_scan_kernel), from B200 measurements of the Sigma shapes at B = 74
+// (profiles/r02_scan_ctas_sweep.txt): the scans are MUFU / MIO-limited, so 16 or 20 resident warps instead of 12 change
+// little — d_state 16 gains 3 % at dt_rank 24 (stage 2, nine blocks) and loses 5-12 % at dt_rank 6 / 48; d_state 4 is
+// flat or slower.  Only that one case leaves the default.
+static int ss2d_pick_ctas(int N, int rp) {
+  return (N == 16 && rp == 24) ? 4 : 3;
+}
 
 size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N) {
   return (size_t)batch * kind_dirs(kind) * D * kMaxSplit * 2 * N * sizeof(float);
@@ -162,23 +170,28 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   p.tiles_per_split = (max_tiles + nsplit - 1) / nsplit;
   p.nsplit = nsplit;
 
+  // register budget (ss2d_scan.cuh): which `__launch_bounds__(128, CTAS)` build runs.  SIGMA_SCAN_CTAS overrides.
+  int rbud = ss2d_pick_ctas(N, pad_rp(R));
+  if (const char *e = getenv("SIGMA_SCAN_CTAS")) rbud = std::max(3, std::min(5, atoi(e)));
+  if (N != 16) rbud = 3;
+  rbud = std::min(rbud, 4);
   {
     // TMA ring depth: as many stages as fit without lowering the register-limited occupancy (227 KB per SM, 1 KB
     // reserved per CTA).
     // Deep rings matter: a tile is requested when the LAST warp releases its slot and needed by the FIRST warp
     // nst-1 tiles later; with 3-4 stages the warps spun on the full barrier ~80 times per tile (ncu, round 1).
     const size_t stage = ((size_t)LT * DT + (size_t)LT * Cp * (kind == SIGMA_DIRS_CROSS ? 2 : 1)) * sizeof(float);
-    // resident CTAs per SM by registers (168 per thread under __launch_bounds__(128, 3)): 3 / 4 / 6 / 12 for 4 / 3 / 2 / 1 warps
-    const int ctas_sm = std::max(Ss2dCfg<16>::CTAS, std::min(12, 65536 / (32 * NW * 168)));
+    // resident CTAs per SM by registers (e.g. 168 per thread under __launch_bounds__(128, 3): 3 / 4 / 6 / 12 for 4 / 3 / 2 / 1 warps)
+    const int ctas_sm = std::max(rbud, std::min(16, 65536 / (32 * NW * ss2d_reg_cap(rbud))));
     const size_t budget = (227 * 1024) / ctas_sm - 1024 - 128;
     p.nst = (int)std::max<size_t>(2, std::min<size_t>(Ss2dCfg<16>::MAX_NST, budget / stage));
     if (const char *e = getenv("SIGMA_SCAN_NST")) p.nst = std::max(2, std::min(Ss2dCfg<16>::MAX_NST, atoi(e)));
   }
   const int nthreads = 32 * NW;
   switch (N) {
-    case 4: return dispatch_rp<4, 1>(p, nthreads, stream);
-    case 8: return dispatch_rp<8, 1>(p, nthreads, stream);
-    case 16: return dispatch_rp<16, 1>(p, nthreads, stream);
+    case 4: return dispatch_rp<4, 1>(p, nthreads, rbud, stream);
+    case 8: return dispatch_rp<8, 1>(p, nthreads, rbud, stream);
+    case 16: return dispatch_rp<16, 1>(p, nthreads, rbud, stream);
   }
   set_error("sigma_ss2d_scan_fwd: d_state=%d unsupported by the fused kernel (4, 8, 16)", N);
   return SIGMA_EUNSUPPORTED;
