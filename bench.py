@@ -485,7 +485,7 @@ def run_train(a):
 
     # the fused core (f1): sigma_ss2d_scan_fwd / sigma_ss2d_scan_bwd on channels-last tensors, same algorithmic-bytes formula
     from sigma_b200 import fused
-    ff0, fb0 = fused.ss2d_scan, ops._call_ss2d_bwd
+    ff0, fs0, fb0 = fused.ss2d_scan, fused.ss2d_scan_save, ops._call_ss2d_bwd
 
     def ffwd_rec(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -496,23 +496,33 @@ def run_train(a):
         rec.append((False, e0, e1, scan_algo_bytes_op(batch, K * D, L, N, K, 4, False)))
         return out
 
-    def fbwd_rec(args):
-        kind, batch, H, W, D, N = args[0], args[15], args[16], args[17], args[18], args[19]
+    def fsave_rec(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        fb0(args)
+        out = fs0(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp)
+        e1.record()
+        K, L = (4, H * W) if kind == _lib.DIRS_CROSS4 else (2, 2 * H * W)
+        rec.append((False, e0, e1, scan_algo_bytes_op(batch, K * D, L, N, K, 4, False)))
+        return out
+
+    def fbwd_rec(args, saved=False):
+        o = 1 if saved else 0
+        kind, batch, H, W, D, N = args[0], args[15 + o], args[16 + o], args[17 + o], args[18 + o], args[19 + o]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fb0(args, saved)
         e1.record()
         K, L = (4, H * W) if kind == _lib.DIRS_CROSS4 else (2, 2 * H * W)
         rec.append((True, e0, e1, scan_algo_bytes_op(batch, K * D, L, N, K, 4, True)))
 
     ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = fwd_rec, bwd_rec
-    fused.ss2d_scan, ops._call_ss2d_bwd = ffwd_rec, fbwd_rec
+    fused.ss2d_scan, fused.ss2d_scan_save, ops._call_ss2d_bwd = ffwd_rec, fsave_rec, fbwd_rec
     try:
         eager_step(rgb, mx, gt, sync=False)
         torch.cuda.synchronize()
     finally:
         ops.selective_scan_cuda_core_fwd, ops.selective_scan_cuda_core_bwd = f0, b0
-        fused.ss2d_scan, ops._call_ss2d_bwd = ff0, fb0
+        fused.ss2d_scan, fused.ss2d_scan_save, ops._call_ss2d_bwd = ff0, fs0, fb0
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -529,7 +539,7 @@ def run_train(a):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     tot_b, tot_ms = agg[False][0] + agg[True][0], agg[False][1] + agg[True][1]
-    roofline = {"bound": "hbm", "kernel": "fused SS2D core (ss2d_scan_kernel forward; ss2d_state_kernel + ss2d_bwd_kernel backward) for SS2D / ConMB, "
+    roofline = {"bound": "hbm", "kernel": "fused SS2D core (ss2d_scan_kernel forward, saving delta' and block-start states; ss2d_bwd_kernel backward) for SS2D / ConMB, "
                                            "op-level scan_op_tma / scan_op_bwd_tma kernels for CroMB"
                 if a.scan_impl == "sigma" else "reference selective_scan_fwd_kernel / selective_scan_bwd_kernel (GPU baseline)",
                 "achieved": round(tot_b / (tot_ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
@@ -550,7 +560,7 @@ def run_train(a):
                    "batch_per_gpu": B, "global_batch": B * world,
                    "parallelism": (f"DDP x{world} (NCCL all-reduce of {gb / 1e6:.0f} MB fp32 gradients per step, "
                                    + ("default 25 MB buckets" if a.ddp_default_buckets else "one bucket aliasing .grad") + ")") if world > 1 else "single GPU",
-                   "path": "fused SS2D core under autograd (sigma_ss2d_scan_fwd / sigma_ss2d_scan_bwd) + torch composition around it" if a.scan_impl == "sigma" else
+                   "path": "fused SS2D core under autograd (sigma_ss2d_scan_fwd_save / sigma_ss2d_scan_bwd_saved) + torch composition around it" if a.scan_impl == "sigma" else
                            "GPU BASELINE: the same composition over the reference's own selective_scan_cuda_core (rebuilt for sm_100a)",
                    "scan_impl": a.scan_impl, "cuda_graph": graph_note, "l2": "256 MiB flush between timed steps",
                    "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)},

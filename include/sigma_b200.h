@@ -143,6 +143,21 @@ int sigma_ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const floa
                         const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
                         int H, int W, int D, int N, int R, int Cp, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Training forward + its backward: `sigma_ss2d_scan_fwd_save` is sigma_ss2d_scan_fwd that also writes what the backward would
+ * otherwise recompute in a state sweep — delta (K, batch, Lseq, D) = softplus(dt_proj) at the position it belongs to, and
+ * hs (sigma_ss2d_scan_hs_bytes) = the scan state at the start of every 16-position block of each direction's walk (the role of
+ * the reference's chunk states `x`, selective_scan_fwd_kernel.cuh:176-190).  `sigma_ss2d_scan_bwd_saved` consumes them (delta
+ * and hs are inputs) and runs only the reverse sweep.  nsplit = 0 lets the library choose the L-segments.  CROSS4 / SEQ2,
+ * d_state 4 / 16. */
+size_t sigma_ss2d_scan_hs_bytes(int kind, int batch, int H, int W, int D, int N);
+int sigma_ss2d_scan_fwd_save(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
+                             const float *Ds, float *y, float *delta, float *hs, int batch, int H, int W, int D, int N, int R, int Cp,
+                             void *workspace, size_t workspace_bytes, int nsplit, void *stream);
+int sigma_ss2d_scan_bwd_saved(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                              const float *dy, const float *delta, const float *hs, float *dxc, float *ddelta, float *dxdbl, float *dA,
+                              float *dDs, float *ddtb, int batch, int H, int W, int D, int N, int R, int Cp, void *workspace,
+                              size_t workspace_bytes, int nsplit, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Row-wise / stencil pieces of a5-a11 (channels-last, fp32; D % 4 == 0, 16-byte aligned rows).
  * ------------------------------------------------------------------------------------------ */

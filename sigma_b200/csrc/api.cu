@@ -261,11 +261,13 @@ int dwconv3x3_silu_launch(const float *x, long long x_row_stride, long long x_ba
 size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N);
 int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
                   const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
-                  size_t ws_bytes, int force_split, cudaStream_t stream);
+                  size_t ws_bytes, int force_split, cudaStream_t stream, float *dsave = nullptr, float *hsave = nullptr);
+size_t ss2d_scan_hs_bytes(int kind, int batch, int H, int W, int D, int N);
 size_t ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, int N);
 int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
                   const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
-                  int H, int W, int D, int N, int R, int Cp, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream);
+                  int H, int W, int D, int N, int R, int Cp, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream,
+                  const float *hs_saved = nullptr);
 int upsample2x_norm_launch(const float *in, const float *gamma, const float *beta, const float *wcls, int ncls, float *out,
                            int B, int Hin, int Win, int C, float eps, cudaStream_t stream);
 int pool_avgmax_partial_launch(const float *x, float *partial, int B, long long L, int C, int nslice, cudaStream_t stream);
@@ -399,6 +401,24 @@ int sigma_ss2d_scan_fwd_split(int kind, const float *xc, const float *xdbl, cons
                        (cudaStream_t)stream);
 }
 
+// training forward: the forward plus what the fused backward needs (delta' slabs, block-start states)
+size_t sigma_ss2d_scan_hs_bytes(int kind, int batch, int H, int W, int D, int N) {
+  if (kind != SIGMA_DIRS_CROSS4 && kind != SIGMA_DIRS_SEQ2) return 0;
+  return ss2d_scan_hs_bytes(kind, batch, H, W, D, N);
+}
+
+int sigma_ss2d_scan_fwd_save(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
+                             const float *Ds, float *y, float *delta, float *hs, int batch, int H, int W, int D, int N, int R, int Cp,
+                             void *workspace, size_t workspace_bytes, int nsplit, void *stream) {
+  int rc = ss2d_check(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp);
+  if (rc) return rc;
+  SIGMA_CHECK_ARG(delta && hs && al16(delta) && al16(hs), "sigma_ss2d_scan_fwd_save: delta / hs must be non-null and 16-byte aligned");
+  SIGMA_CHECK_ARG(kind == SIGMA_DIRS_CROSS4 || kind == SIGMA_DIRS_SEQ2, "sigma_ss2d_scan_fwd_save: kind %d unsupported (CROSS4, SEQ2)", kind);
+  SIGMA_CHECK_ARG(N == 4 || N == 16, "sigma_ss2d_scan_fwd_save: d_state=%d unsupported (4, 16)", N);
+  return ss2d_scan_fwd(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp, workspace, workspace_bytes, nsplit,
+                       (cudaStream_t)stream, delta, hs);
+}
+
 size_t sigma_ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, int N) {
   if (kind != SIGMA_DIRS_CROSS4 && kind != SIGMA_DIRS_SEQ2) return 0;
   return ss2d_scan_bwd_workspace_bytes(kind, batch, H, W, D, N);
@@ -406,15 +426,27 @@ size_t sigma_ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, in
 
 static int ss2d_bwd_entry(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
                           const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb,
-                          int batch, int H, int W, int D, int N, int R, int Cp, void *ws, size_t wsb, int nsplit, void *stream) {
+                          int batch, int H, int W, int D, int N, int R, int Cp, void *ws, size_t wsb, int nsplit, void *stream,
+                          const float *hs_saved = nullptr) {
   SIGMA_CHECK_ARG(xc && xdbl && dtw && dtb && A && Ds && dy && delta && dxc && ddelta && dxdbl && dA && dDs && ddtb, "sigma_ss2d_scan_bwd: null pointer");
   SIGMA_CHECK_ARG(kind == SIGMA_DIRS_CROSS4 || kind == SIGMA_DIRS_SEQ2, "sigma_ss2d_scan_bwd: kind %d unsupported (CROSS4, SEQ2)", kind);
   SIGMA_CHECK_ARG(batch > 0 && H > 0 && W > 0 && D > 0 && D % 64 == 0 && R > 0, "sigma_ss2d_scan_bwd: bad sizes (D=%d must be a multiple of 64)", D);
   SIGMA_CHECK_ARG(N == 4 || N == 16, "sigma_ss2d_scan_bwd: d_state=%d unsupported (4, 16)", N);
   SIGMA_CHECK_ARG(Cp == sigma_ss2d_padded_cp(N, R), "sigma_ss2d_scan_bwd: Cp=%d must equal sigma_ss2d_padded_cp(N=%d, R=%d)", Cp, N, R);
   SIGMA_CHECK_ARG(al16(xc) && al16(xdbl) && al16(dy) && al16(delta) && al16(dxc) && al16(ddelta) && al16(dxdbl), "sigma_ss2d_scan_bwd: pointers must be 16-byte aligned");
+  SIGMA_CHECK_ARG(hs_saved == nullptr || al16(hs_saved), "sigma_ss2d_scan_bwd_saved: hs must be 16-byte aligned");
   return ss2d_scan_bwd(kind, xc, xdbl, dtw, dtb, A, Ds, dy, delta, dxc, ddelta, dxdbl, dA, dDs, ddtb, batch, H, W, D, N, R, Cp, ws, wsb, nsplit,
-                       (cudaStream_t)stream);
+                       (cudaStream_t)stream, hs_saved);
+}
+
+// backward after sigma_ss2d_scan_fwd_save: `delta` and `hs` are INPUTS (what that call wrote); no state sweep runs
+int sigma_ss2d_scan_bwd_saved(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
+                              const float *dy, const float *delta, const float *hs, float *dxc, float *ddelta, float *dxdbl, float *dA,
+                              float *dDs, float *ddtb, int batch, int H, int W, int D, int N, int R, int Cp, void *workspace,
+                              size_t workspace_bytes, int nsplit, void *stream) {
+  SIGMA_CHECK_ARG(hs != nullptr, "sigma_ss2d_scan_bwd_saved: null hs");
+  return ss2d_bwd_entry(kind, xc, xdbl, dtw, dtb, A, Ds, dy, const_cast<float *>(delta), dxc, ddelta, dxdbl, dA, dDs, ddtb, batch, H, W, D, N, R,
+                        Cp, workspace, workspace_bytes, nsplit, stream, hs);
 }
 
 int sigma_ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,

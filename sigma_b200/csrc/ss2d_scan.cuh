@@ -48,11 +48,17 @@ struct alignas(64) Ss2dParams {
   CUtensorMap m_xc[4], m_dbl[4];
   const float *dtw, *dtb, *A, *Ds;
   float *y, *carry;
+  // training forward (SAVE kernels): what the fused backward (ss2d_scan_bwd.cu) would otherwise recompute in its state sweep —
+  // delta' = softplus(dt_proj) slabs (K, batch, Lseq, D), stored like y, and the state at the start of every 16-position block
+  // of the walk, hsave (K, batch, save_tiles, D, N) indexed by the backward's walk-order tile number
+  float *dsave, *hsave;
+  int save_tiles;
   int D, N, R, Cp, kind, batch, ndir;
   long long Lseq;
   int I[4], O[4], rev[4];
   long long istride[4], ostride[4];   // y element strides of the inner / outer walk index
   int nsplit, tiles_per_split;
+  int npoly;   // d_state 16: state pairs per position whose exponential runs on the FMA pipe (0, 1, 2)
   int nst;     // TMA ring depth: as many LT-position stages as fit next to CTAS-1 other CTAs in shared memory
   int ablate;  // timing experiments, only in builds with -DSIGMA_SCAN_ABLATION (SIGMA_SCAN_ABLATE env):
                // 1 = no y store, 2 = no per-group prologue, 4 = no TMA reload
@@ -79,6 +85,27 @@ struct Ss2dThread {
   bool ok[CPT];
   int ablate;
 };
+
+// 2^x for a PAIR of x <= 0 on the FMA / ALU pipes instead of the SFU (the d_state-16 scans are MUFU-bound: 17 MUFU per channel
+// and position at 16 lanes per clock and SM): round to nearest integer with the 1.5·2^23 trick, degree-5 polynomial for 2^f on
+// [-0.5, 0.5] (max relative error 2.4e-7, the level of MUFU.EX2), exponent added into the bit pattern.  3 FADD2 + 5 FFMA2 on the
+// FMA pipe, 2 FMNMX + 2 LEA on the ALU pipe per pair.
+__device__ __forceinline__ f2 ex2_poly2(f2 x) {
+  x.x = fmaxf(x.x, -125.f); x.y = fmaxf(x.y, -125.f);          // keep the exponent field in range; 2^-125 ~ 0
+  const f2 magic = f2{12582912.f, 12582912.f};
+  unsigned long long t, r, f;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pack2(x.x, x.y)), "l"(pack2(magic.x, magic.y)));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(t), "l"(pack2(magic.x, magic.y)));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(pack2(x.x, x.y)), "l"(r));
+  const f2 ff = unpack2(f);
+  f2 p = fma2(f2{0.0013390863314270973f, 0.0013390863314270973f}, ff, f2{0.009676031768321991f, 0.009676031768321991f});
+  p = fma2(p, ff, f2{0.055503569543361664f, 0.055503569543361664f});
+  p = fma2(p, ff, f2{0.2402210682630539f, 0.2402210682630539f});
+  p = fma2(p, ff, f2{0.6931471824645996f, 0.6931471824645996f});
+  p = fma2(p, ff, f2{1.0000001192092896f, 1.0000001192092896f});
+  const f2 tt = unpack2(t);
+  return f2{__int_as_float(__float_as_int(p.x) + (__float_as_int(tt.x) << 23)), __int_as_float(__float_as_int(p.y) + (__float_as_int(tt.y) << 23))};
+}
 
 // packed helpers on raw 64-bit register pairs (keep loop-invariant pairs paired: no MOVs to rebuild them)
 __device__ __forceinline__ unsigned long long fma2_raw(unsigned long long a, unsigned long long b, unsigned long long c) {
@@ -149,10 +176,10 @@ __device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, 
 // channel lies beyond D walks a one-element sink instead (kernel prologue), so there is no branch around the store.
 // Per position B and C are read ONCE (2·N/4 broadcast LDS.128) and reused by the CPT channels of the thread;
 // per channel and state pair: FMUL2 (exp arguments), 2 x MUFU.EX2, FMUL2 (delta·u·B), FFMA2 (h), FFMA2 (C·h).
-template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL>
+template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL, bool SAVE = false, int NPOLY = 0>
 __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *rb, const float *rc, float *yq,
                                            int ystep, int ycstride, const float (&dl)[CPT][G],
-                                           const float (&u)[CPT][G], int cnt) {
+                                           const float (&u)[CPT][G], int cnt, float *dq = nullptr) {
   constexpr int Cp = 2 * N + RP;
   constexpr int NCH = N >= 8 ? 2 : 1;   // independent C·h accumulator chains per channel
 #pragma unroll
@@ -174,7 +201,9 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
           for (int hp = 0; hp < 2; ++hp) {                                   // state pair (4·s4 + 2·hp, +1)
             const int s = 4 * s4 + 2 * hp;
             const f2 arg = mul2(f2{d, d}, f2{t.a2[c][s], t.a2[c][s + 1]});
-            const f2 a = f2{ex2(arg.x), ex2(arg.y)};
+            // NPOLY of the N/2 state pairs take their exponentials from the FMA pipe (ex2_poly2), the rest from MUFU.EX2
+            const f2 a = (NPOLY > 0 && (s >> 1) % (N / 2 / (NPOLY > 0 ? NPOLY : 1)) == 0 && (s >> 1) / (N / 2 / (NPOLY > 0 ? NPOLY : 1)) < NPOLY)
+                             ? ex2_poly2(arg) : f2{ex2(arg.x), ex2(arg.y)};
             const f2 bb = mul2(f2{du, du}, hp == 0 ? f2{bv.x, bv.y} : f2{bv.z, bv.w});
             const f2 hn = fma2(a, f2{t.h[c][s], t.h[c][s + 1]}, bb);
             t.h[c][s] = hn.x; t.h[c][s + 1] = hn.y;
@@ -194,12 +223,14 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
           if (NCH == 2) y += yacc[c][1].x + yacc[c][1].y;
           if (SIGMA_ABL(t.ablate, 1)) t.sumdl[c] += y;
           else yq[c * ycstride] = fmaf(t.Dv[c], u[c][i], y);
+          if (SAVE) dq[c * ycstride] = dl[c][i];
         } else {
           t.sumdl[c] += dl[c][i];
         }
       }
     }
     if (WITH_Y) yq += ystep;
+    if (SAVE) dq += ystep;
   }
 }
 
@@ -212,6 +243,10 @@ struct Ss2dWalk {
   float *ybase;
   long long istride, ostride;
   int ystep;   // y elements from one walked position to the next (sign follows the walk direction; 0 on the sink)
+  float *dbase;        // SAVE: this thread's channel in the delta' slab of (k, b) (same addressing as ybase)
+  float *hs_base;      // SAVE: hsave + (((k·batch + b)·save_tiles)·D + d)·N; tile tau16 adds tau16·D·N
+  long long hs_stride; // D·N (0 on the sink)
+  int TPO16, ntiles16; // 16-position blocks per inner walk line / in the whole walk (the backward's tile geometry)
   int stage_fl, xc_fl, dbl_fl, DT, nwarps, lane, ch;
   int t0, t1, TPO, ntiles, I, nst;
   bool cross, rev;
@@ -220,7 +255,7 @@ struct Ss2dWalk {
 // The tile loop of one warp.  The software pipeline over groups of G positions runs ACROSS tiles: while the
 // recurrence of group g runs, delta'/u of group g+1 are computed — from the next tile's ring slot when g is the
 // last group of its tile — so no prologue is exposed at a tile boundary and none is computed twice.
-template <int N, int CPT, int RP, bool WITH_Y, bool REV, typename Request>
+template <int N, int CPT, int RP, bool WITH_Y, bool REV, bool SAVE, int NPOLY, typename Request>
 __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2dWalk<N, CPT, RP> &w, Request &&request_tile) {
   constexpr int G = Ss2dCfg<N>::G, LT = Ss2dCfg<N>::LT;
   constexpr int Cp = 2 * N + RP;
@@ -228,7 +263,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
 
   // ring slot / phase and (outer index, inner tile) of the tile being opened advance incrementally: no division
   // or modulo per tile.  Tiles are walked in ascending tau; reversed directions map tau -> ntiles-1-tau.
-  struct Tile { const float *sXC, *sDB, *sDC; float *ystart; int npos, ng; };   // ystart: y of the tile's first WALKED group start
+  struct Tile { const float *sXC, *sDB, *sDC; float *ystart, *dstart; int npos, ng, tm16; };   // ystart: y of the tile's first WALKED group start
   int ost = 0, oph = 0;                                  // slot and phase parity of the next tile to open
   int tm0 = w.rev ? w.ntiles - 1 - w.t0 : w.t0;          // memory-order tile index of tile t0
   int oo = tm0 / w.TPO, oti = tm0 - oo * w.TPO;          // its (outer index, inner tile)
@@ -241,7 +276,10 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
     const int i0 = oti * LT;
     T.npos = min(LT, w.I - i0);
     T.ng = (T.npos + G - 1) / G;
-    T.ystart = w.ybase + (long long)oo * w.ostride + (long long)(i0 + (REV ? T.ng * G - 1 : 0)) * w.istride;
+    const long long yoff = (long long)oo * w.ostride + (long long)(i0 + (REV ? T.ng * G - 1 : 0)) * w.istride;
+    T.ystart = w.ybase + yoff;
+    T.dstart = SAVE ? w.dbase + yoff : nullptr;
+    T.tm16 = SAVE ? oo * w.TPO16 + (i0 >> 4) : 0;      // memory-order index of the tile's first 16-position block
     if (++ost == w.nst) { ost = 0; oph ^= 1; }
     if (w.rev) { if (--oti < 0) { oti = w.TPO - 1; --oo; } }
     else       { if (++oti == w.TPO) { oti = 0; ++oo; } }
@@ -257,6 +295,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
   int rst = 0;                    // ring slot of the tile being processed
   const int gstep = G * w.ystep;  // y elements from one group's first walked position to the next group's
   float *yp = cur.ystart;         // running y pointer: first walked position of the current group
+  float *dp = cur.dstart;
   for (int tau = w.t0; tau < w.t1; ++tau) {
     Tile nxt = cur;
     int jn = j;
@@ -283,6 +322,16 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
       const float *rc = cur.sDC + j * G * Cp + N;
       // prologue(next) and body(current) are independent; keeping them in ONE basic block lets ptxas interleave
       // the prologue's FMA/LG2 work with the body's exponentials (it does not schedule across the cnt branch)
+      if (SAVE) {
+        // state entering a 16-position block of the walk (the backward's tile start): the block's first walked group
+        const bool first = REV ? ((((j + 1) * G) & 15) == 0 || j == cur.ng - 1) : (((j * G) & 15) == 0);
+        if (first && t.ok[0]) {
+          const int tm16 = cur.tm16 + ((j * G) >> 4);
+          float4 *hp = reinterpret_cast<float4 *>(w.hs_base + (long long)(REV ? w.ntiles16 - 1 - tm16 : tm16) * w.hs_stride);
+#pragma unroll
+          for (int q = 0; q < N / 4; ++q) hp[q] = make_float4(t.h[0][4 * q], t.h[0][4 * q + 1], t.h[0][4 * q + 2], t.h[0][4 * q + 3]);
+        }
+      }
       if (cnt >= G) {
         if (!SIGMA_ABL(t.ablate, 2)) group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
         else {
@@ -291,10 +340,10 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
 #pragma unroll
             for (int i = 0; i < G; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
         }
-        group_body<N, CPT, RP, G, WITH_Y, REV, true>(t, rb, rc, yp, w.ystep, ycs, dl, u, G);
+        group_body<N, CPT, RP, G, WITH_Y, REV, true, SAVE, NPOLY>(t, rb, rc, yp, w.ystep, ycs, dl, u, G, dp);
       } else {
         group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
-        group_body<N, CPT, RP, G, WITH_Y, REV, false>(t, rb, rc, yp, w.ystep, ycs, dl, u, cnt);
+        group_body<N, CPT, RP, G, WITH_Y, REV, false, SAVE, NPOLY>(t, rb, rc, yp, w.ystep, ycs, dl, u, cnt, dp);
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
@@ -302,6 +351,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
         for (int i = 0; i < G; ++i) { dl[c][i] = dln[c][i]; u[c][i] = un[c][i]; }
       j = jn;
       yp += gstep;
+      if (SAVE) dp += gstep;
     }
     // this warp is done with the ring slot; the last of the CTA's warps to get here refills it
     __syncwarp();
@@ -312,11 +362,13 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
     if (++rst == w.nst) rst = 0;
     cur = nxt;
     yp = cur.ystart;
+    dp = cur.dstart;
   }
 }
 
-template <int N, int CPT, int RP, int MODE, int CTAS>
+template <int N, int CPT, int RP, int MODE, int CTAS, bool SAVE = false, int NPOLY = 0>
 __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
+  static_assert(!SAVE || MODE != MODE_SUMMARY, "the summary pass has no final states to save");
   constexpr int LT = Ss2dCfg<N>::LT;
   constexpr bool WITH_Y = MODE != MODE_SUMMARY;
   const int NST = p.nst;
@@ -417,13 +469,21 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, CTAS) ss2d_scan_kernel(
     w.istride = 0; w.ostride = 0;
   }
   w.ystep = (int)(rev ? -w.istride : w.istride);
+  w.dbase = nullptr; w.hs_base = nullptr; w.hs_stride = 0; w.TPO16 = 0; w.ntiles16 = 0;
+  if (SAVE) {
+    w.dbase = t.ok[0] ? p.dsave + (w.ybase - p.y) : w.ybase;          // same (K, batch, Lseq, D) addressing as y; sink otherwise
+    w.TPO16 = (I + 15) >> 4;
+    w.ntiles16 = O * w.TPO16;
+    w.hs_stride = (long long)p.D * N;
+    w.hs_base = p.hsave + ((((long long)k * p.batch + b) * p.save_tiles) * p.D + min(d0 + tid, p.D - 1)) * N;
+  }
   w.stage_fl = stage_fl; w.xc_fl = xc_fl; w.dbl_fl = dbl_fl; w.DT = DT;
   w.nwarps = NTC >> 5; w.lane = tid & 31; w.ch = tid;
   w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I; w.nst = NST;
   w.cross = cross; w.rev = rev;
 
-  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true>(t, w, request_tile);
-  else     walk_tiles<N, CPT, RP, WITH_Y, false>(t, w, request_tile);
+  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true, SAVE, NPOLY>(t, w, request_tile);
+  else     walk_tiles<N, CPT, RP, WITH_Y, false, SAVE, NPOLY>(t, w, request_tile);
 
   if (MODE == MODE_SUMMARY || SIGMA_ABL(p.ablate, 1)) {
 #pragma unroll

@@ -441,10 +441,17 @@ constexpr int kFbMaxSplit = 64;
 
 static size_t fb_al(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static int fb_max_tiles(int kind, int H, int W) {
+int ss2d_save_tiles(int kind, int H, int W);
+static int fb_max_tiles(int kind, int H, int W) { return ss2d_save_tiles(kind, H, W); }
+int ss2d_save_tiles(int kind, int H, int W) {
   const long long L = (long long)H * W;
   if (kind == SIGMA_DIRS_SEQ2) return (int)((2 * L + FB_LT - 1) / FB_LT);
   return (int)std::max<long long>((L + FB_LT - 1) / FB_LT, (long long)W * ((H + FB_LT - 1) / FB_LT));
+}
+
+size_t ss2d_scan_hs_bytes(int kind, int batch, int H, int W, int D, int N) {
+  const int K = kind == SIGMA_DIRS_CROSS4 ? 4 : 2;
+  return (size_t)K * batch * fb_max_tiles(kind, H, W) * D * N * sizeof(float);
 }
 
 // workspace = [hs (K, batch, max_tiles, D, N)] [forward carries] [reverse carries]
@@ -458,7 +465,8 @@ size_t ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, i
 // (batch, Lseq, K, Cp) are ACCUMULATED INTO after being zeroed here; dA (K·D, N), dDs (K·D), ddtb (K, D) overwritten.
 int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
                   const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
-                  int H, int W, int D, int N, int R, int Cp, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream) {
+                  int H, int W, int D, int N, int R, int Cp, void *ws, size_t ws_bytes, int force_split, cudaStream_t stream,
+                  const float *hs_saved) {
   if (ws == nullptr || ws_bytes < ss2d_scan_bwd_workspace_bytes(kind, batch, H, W, D, N)) {
     set_error("sigma_ss2d_scan_bwd: workspace too small (%zu < %zu)", ws_bytes, ss2d_scan_bwd_workspace_bytes(kind, batch, H, W, D, N));
     return SIGMA_EWORKSPACE;
@@ -474,7 +482,7 @@ int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw
   const size_t hs_b = fb_al((size_t)K * batch * p.max_tiles * D * N * sizeof(float));
   const size_t carry_b = fb_al((size_t)batch * K * D * kFbMaxSplit * 2 * N * sizeof(float));
   p.hs = (float *)ws;
-  p.hs_in = p.hs;
+  p.hs_in = hs_saved ? hs_saved : p.hs;   // hs_saved: the training forward already wrote delta' and the block-start states
   float *fcarry = (float *)((char *)ws + hs_b), *rcarry = (float *)((char *)ws + hs_b + carry_b);
   const int CPW = N >= 16 ? 16 : 32;
   int rc, max_tiles = 0;
@@ -560,7 +568,9 @@ int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw
     };
     int r;
     ps.carry = fcarry;
-    if (pm.nsplit == 1) {
+    if (hs_saved != nullptr) {
+      // nothing to recompute
+    } else if (pm.nsplit == 1) {
       if ((r = run(ss2d_state_kernel<NN, MODE_SERIAL>, ps, st_smem))) return r;
     } else {
       if ((r = run(ss2d_state_kernel<NN, MODE_SUMMARY>, ps, st_smem))) return r;

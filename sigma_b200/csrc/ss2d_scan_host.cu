@@ -88,6 +88,8 @@ static int pick_warps(int D, int cpt, int maxw) {
 
 constexpr int kMaxSplit = 32;
 
+int ss2d_save_tiles(int kind, int H, int W);   // ss2d_scan_bwd.cu: 16-position blocks of the longest walk
+
 // Which register budget to run (`CTAS` of ss2d_scan_kernel), from B200 measurements of the Sigma shapes at B = 74
 // (profiles/r02_scan_ctas_sweep.txt): the scans are MUFU / MIO-limited, so 16 or 20 resident warps instead of 12 change
 // little — d_state 16 gains 3 % at dt_rank 24 (stage 2, nine blocks) and loses 5-12 % at dt_rank 6 / 48; d_state 4 is
@@ -102,14 +104,16 @@ size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N) {
 
 int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A,
                   const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
-                  size_t ws_bytes, int force_split, cudaStream_t stream) {
+                  size_t ws_bytes, int force_split, cudaStream_t stream, float *dsave, float *hsave) {
   Ss2dParams p;
   memset(&p, 0, sizeof(p));
   p.dtw = dtw; p.dtb = dtb; p.A = A; p.Ds = Ds; p.y = y; p.carry = (float *)ws;
   p.D = D; p.N = N; p.R = R; p.Cp = Cp; p.kind = kind; p.batch = batch;
+  p.dsave = dsave; p.hsave = hsave; p.save_tiles = hsave ? ss2d_save_tiles(kind, H, W) : 0;
   const int ndir = kind_dirs(kind);
   p.ndir = ndir;
   if (const char *e = getenv("SIGMA_SCAN_ABLATE")) p.ablate = atoi(e);
+  if (const char *e = getenv("SIGMA_SCAN_NPOLY")) p.npoly = std::max(0, std::min(2, atoi(e)));
   const int K = kind == SIGMA_DIRS_CROSS ? 1 : ndir;        // x_dbl rows per position
   const long long Lseq = kind == SIGMA_DIRS_SEQ2 ? 2LL * H * W : (long long)H * W;
   p.Lseq = Lseq;

@@ -169,6 +169,23 @@ def ss2d_scan(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
     return y
 
 
+def ss2d_scan_save(kind, xc, xdbl, dtw, dtb, A, Ds, batch, H, W, D, N, R, Cp):
+    """Training forward: ss2d_scan that also returns delta' (K, batch, Lseq, D) and the block-start states `hs` for
+    sigma_ss2d_scan_bwd_saved (no state sweep in the backward)."""
+    L_ = _lib.lib()
+    ndir = {_lib.DIRS_CROSS4: 4, _lib.DIRS_SEQ2: 2}[kind]
+    Lseq = 2 * H * W if kind == _lib.DIRS_SEQ2 else H * W
+    y = torch.empty((ndir, batch, Lseq, D), dtype=torch.float32, device=xc.device)
+    delta = torch.empty_like(y)
+    hs = torch.empty(L_.sigma_ss2d_scan_hs_bytes(kind, batch, H, W, D, N) // 4, dtype=torch.float32, device=xc.device)
+    wsb = L_.sigma_ss2d_scan_workspace_bytes(kind, batch, H, W, D, N)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=xc.device)
+    rc = L_.sigma_ss2d_scan_fwd_save(kind, _p(xc), _p(xdbl), _p(dtw), _p(dtb), _p(A), _p(Ds), _p(y), _p(delta), _p(hs), batch, H, W, D,
+                                     N, R, Cp, _p(ws), wsb, int(_FORCE_SPLIT or 0), _stream())
+    _lib.check(rc, "sigma_ss2d_scan_fwd_save")
+    return y, delta, hs
+
+
 def merge_norm_gate(y, K, k_stride, in_batch_stride, ln, z, z_row_stride, gate, out, out_batch_stride, out_row_stride,
                     rows, rows_per_batch, D, y_offset=0, out_offset=0):
     yp = ctypes.c_void_p(y.data_ptr() + 4 * y_offset)

@@ -333,10 +333,16 @@ def fused_core_ok(xc, D, N):
     return FUSED_TRAINING and xc.is_cuda and N in (4, 16) and D % 64 == 0
 
 
-def _call_ss2d_bwd(args):
+FUSED_SAVE_STATES = True      # training forward keeps delta' and the block-start states, so the backward runs no state sweep
+
+
+def _call_ss2d_bwd(args, saved=False):
     """The native call of the fused backward (a module-level function so that bench.py can bracket it with events)."""
     from . import fused
     L_ = _lib.lib()
+    if saved:
+        _lib.check(L_.sigma_ss2d_scan_bwd_saved(*args, int(fused._FORCE_SPLIT or 0), _stream()), "sigma_ss2d_scan_bwd_saved")
+        return
     if fused._FORCE_SPLIT:
         rc = L_.sigma_ss2d_scan_bwd_split(*args, int(fused._FORCE_SPLIT), _stream())
     else:
@@ -364,8 +370,12 @@ class FusedSS2DCore(torch.autograd.Function):
         dtw, dtb = dt_projs_weight.contiguous(), dt_projs_bias.contiguous()
         A = (-torch.exp(A_logs)).contiguous()
         Dsc = Ds.contiguous()
-        y = fused.ss2d_scan(kind, xc, xdbl, dtw, dtb, A, Dsc, B, H, W, D, N, R, Cp)                                  # (K, B, Lseq, D)
-        ctx.save_for_backward(xc, xdbl, xw, dtw, dtb, A, Dsc)
+        if FUSED_SAVE_STATES:
+            y, delta, hs = fused.ss2d_scan_save(kind, xc, xdbl, dtw, dtb, A, Dsc, B, H, W, D, N, R, Cp)
+            ctx.save_for_backward(xc, xdbl, xw, dtw, dtb, A, Dsc, delta, hs)
+        else:
+            y = fused.ss2d_scan(kind, xc, xdbl, dtw, dtb, A, Dsc, B, H, W, D, N, R, Cp)                              # (K, B, Lseq, D)
+            ctx.save_for_backward(xc, xdbl, xw, dtw, dtb, A, Dsc)
         ctx.meta = (kind, H, W, K, D, N, R, Cp)
         return y.sum(0)
 
@@ -373,12 +383,17 @@ class FusedSS2DCore(torch.autograd.Function):
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, dy):
         from . import fused
-        xc, xdbl, xw, dtw, dtb, A, Ds = ctx.saved_tensors
+        saved = len(ctx.saved_tensors) == 9
+        if saved:
+            xc, xdbl, xw, dtw, dtb, A, Ds, delta, hs = ctx.saved_tensors
+        else:
+            xc, xdbl, xw, dtw, dtb, A, Ds = ctx.saved_tensors
         kind, H, W, K, D, N, R, Cp = ctx.meta
         B, Lseq, _ = xc.shape
         dy = dy.contiguous().float()
         dev = xc.device
-        delta = torch.empty((K, B, Lseq, D), dtype=torch.float32, device=dev)
+        if not saved:
+            delta = torch.empty((K, B, Lseq, D), dtype=torch.float32, device=dev)
         ddelta = torch.empty_like(delta)
         dxc = torch.empty((B, Lseq, D), dtype=torch.float32, device=dev)
         dxdbl = torch.empty((B * Lseq, K, Cp), dtype=torch.float32, device=dev)
@@ -388,9 +403,9 @@ class FusedSS2DCore(torch.autograd.Function):
         L_ = _lib.lib()
         wsb = L_.sigma_ss2d_scan_bwd_workspace_bytes(kind, B, H, W, D, N)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
-        args = (kind, _ptr(xc), _ptr(xdbl), _ptr(dtw), _ptr(dtb), _ptr(A), _ptr(Ds), _ptr(dy), _ptr(delta), _ptr(dxc), _ptr(ddelta),
-                _ptr(dxdbl), _ptr(dA), _ptr(dDs), _ptr(ddtb), B, H, W, D, N, R, Cp, _ptr(ws), wsb)
-        _call_ss2d_bwd(args)
+        head = (kind, _ptr(xc), _ptr(xdbl), _ptr(dtw), _ptr(dtb), _ptr(A), _ptr(Ds), _ptr(dy), _ptr(delta))
+        tail = (_ptr(dxc), _ptr(ddelta), _ptr(dxdbl), _ptr(dA), _ptr(dDs), _ptr(ddtb), B, H, W, D, N, R, Cp, _ptr(ws), wsb)
+        _call_ss2d_bwd(head + ((_ptr(hs),) if saved else ()) + tail, saved)
         # dt_proj: d dt_r = ddelta_k · W_dt[k]  (into the dt_r columns of dxdbl),  dW_dt[k] = ddelta_k^T · dt_r_k
         xd3 = xdbl.view(B * Lseq, K, Cp)
         dW = torch.empty_like(dtw)

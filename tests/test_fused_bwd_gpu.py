@@ -1,5 +1,5 @@
 """GPU: f1 — the fused SS2D core under autograd (ops.FusedSS2DCore: x_proj GEMM + sigma_ss2d_scan_fwd forward,
-sigma_ss2d_scan_bwd backward) against the composed path (CrossScan + einsums + the op-level scan kernels, itself pinned to the
+sigma_ss2d_scan_bwd backward; and the state-saving pair sigma_ss2d_scan_fwd_save / sigma_ss2d_scan_bwd_saved) against the composed path (CrossScan + einsums + the op-level scan kernels, itself pinned to the
 reference's autograd goldens): output and EVERY gradient, kinds CROSS4 (SS2D) and SEQ2 (ConMB), ragged maps, 1 / 3 / auto
 L-segments.  fp32-grade projections on both sides (TF32 off); bar 1e-3 of each tensor's scale."""
 import numpy as np
@@ -27,10 +27,13 @@ def _cmp(name, got, ref, bar=1e-3):
     assert err <= bar, f"{name}: {err:.2e} of its scale"
 
 
-@pytest.mark.parametrize("B,H,W,D,N,R", [(2, 6, 5, 64, 16, 2), (1, 30, 40, 128, 16, 8), (2, 9, 13, 64, 4, 4), (1, 17, 33, 192, 16, 6)])
+@pytest.mark.parametrize("B,H,W,D,N,R", [(2, 6, 5, 64, 16, 2), (1, 30, 40, 128, 16, 8), (2, 9, 13, 64, 4, 4), (1, 17, 33, 192, 16, 6),
+                                         (1, 40, 21, 64, 4, 4)])
 @pytest.mark.parametrize("split", [0, 1, 3])
-def test_fused_core_cross4_matches_composed(B, H, W, D, N, R, split):
+@pytest.mark.parametrize("save", [True, False])   # True: forward keeps delta' / block-start states (sigma_ss2d_scan_fwd_save + _bwd_saved)
+def test_fused_core_cross4_matches_composed(B, H, W, D, N, R, split, save, monkeypatch):
     from sigma_b200 import _lib, fused, ops
+    monkeypatch.setattr(ops, "FUSED_SAVE_STATES", save)
     torch.backends.cuda.matmul.allow_tf32 = False
     tag = f"fb4/{B}/{H}/{W}/{D}/{N}/{R}"
     xc0 = P.randn(S, tag + "/xc", (B, H * W, D)).cuda()
@@ -58,8 +61,10 @@ def test_fused_core_cross4_matches_composed(B, H, W, D, N, R, split):
 
 @pytest.mark.parametrize("B,H,W,D,N,R", [(2, 6, 5, 64, 4, 2), (1, 15, 20, 128, 4, 12)])
 @pytest.mark.parametrize("split", [0, 2])
-def test_fused_core_seq2_matches_composed(B, H, W, D, N, R, split):
+@pytest.mark.parametrize("save", [True, False])
+def test_fused_core_seq2_matches_composed(B, H, W, D, N, R, split, save, monkeypatch):
     from sigma_b200 import _lib, fused, ops
+    monkeypatch.setattr(ops, "FUSED_SAVE_STATES", save)
     torch.backends.cuda.matmul.allow_tf32 = False
     tag = f"fb2/{B}/{H}/{W}/{D}/{N}/{R}"
     L = H * W
@@ -85,3 +90,51 @@ def test_fused_core_seq2_matches_composed(B, H, W, D, N, R, split):
     _cmp("y", y.detach(), y_ref.detach())
     for nm, g, r in zip(["dxc", "dx_proj_weight", "ddt_projs_weight", "ddt_projs_bias", "dA_logs", "dDs"], [x_f.grad] + [t.grad for t in pr], ref):
         _cmp(f"{tag} split={split} {nm}", g, r)
+
+
+@pytest.mark.parametrize("kind_name,B,H,W,D,N,R", [("cross4", 2, 9, 13, 64, 4, 4), ("cross4", 1, 40, 21, 64, 4, 4), ("cross4", 1, 17, 33, 128, 16, 6),
+                                                   ("seq2", 2, 7, 9, 64, 4, 3)])
+@pytest.mark.parametrize("split", [0, 3])
+def test_saved_states_equal_the_state_sweep(kind_name, B, H, W, D, N, R, split):
+    """delta' and the block-start states written by the training forward (sigma_ss2d_scan_fwd_save) against the ones the backward's
+    own state sweep (ss2d_state_kernel, inside sigma_ss2d_scan_bwd) leaves in its scratch / workspace."""
+    import ctypes
+    from sigma_b200 import _lib, fused
+    L_ = _lib.lib()
+    kind = _lib.DIRS_CROSS4 if kind_name == "cross4" else _lib.DIRS_SEQ2
+    K = 4 if kind_name == "cross4" else 2
+    Lseq = H * W if kind_name == "cross4" else 2 * H * W
+    tag = f"sv/{kind_name}/{B}/{H}/{W}/{D}/{N}/{R}"
+    Cp = L_.sigma_ss2d_padded_cp(N, R)
+    xc = P.randn(S, tag + "/xc", (B, Lseq, D)).cuda()
+    xdbl = P.randn(S, tag + "/xdbl", (B, Lseq, K, Cp)).cuda()
+    dtw = P.rand(S, tag + "/dtw", (K, D, R), -R ** -0.5, R ** -0.5).cuda()
+    dtb = P.rand(S, tag + "/dtb", (K, D), -5.0, -1.0).cuda()
+    A = -P.rand(S, tag + "/A", (K * D, N), 0.5, N + 0.5).cuda()
+    Ds = P.randn(S, tag + "/Ds", (K * D,)).cuda()
+    fused._FORCE_SPLIT = split
+    try:
+        y, delta, hs = fused.ss2d_scan_save(kind, xc, xdbl, dtw, dtb, A, Ds, B, H, W, D, N, R, Cp)
+        y0 = fused.ss2d_scan(kind, xc, xdbl, dtw, dtb, A, Ds, B, H, W, D, N, R, Cp)
+    finally:
+        fused._FORCE_SPLIT = 0
+    assert torch.equal(y, y0), "the state-saving forward must not change y"
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    dy = P.randn(S, tag + "/dy", (B, Lseq, D)).cuda()
+    delta2 = torch.zeros_like(delta)
+    ddelta, dxc = torch.empty_like(delta), torch.empty_like(xc)
+    dxdbl = torch.empty_like(xdbl)
+    dA, dDs, ddtb = torch.empty_like(A), torch.empty_like(Ds), torch.empty_like(dtb)
+    wsb = L_.sigma_ss2d_scan_bwd_workspace_bytes(kind, B, H, W, D, N)
+    ws = torch.zeros(wsb, dtype=torch.uint8, device="cuda")
+    rc = L_.sigma_ss2d_scan_bwd_split(kind, p(xc), p(xdbl), p(dtw), p(dtb), p(A), p(Ds), p(dy), p(delta2), p(dxc), p(ddelta), p(dxdbl), p(dA),
+                                      p(dDs), p(ddtb), B, H, W, D, N, R, Cp, p(ws), wsb, split, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "sigma_ss2d_scan_bwd_split")
+    torch.cuda.synchronize()
+    _cmp("delta'", delta, delta2, 1e-5)
+    hs2 = ws[: hs.numel() * 4].view(torch.float32)
+    # blocks no direction reaches (max_tiles is the longest walk's count) stay unwritten on both sides: compare where the sweep wrote
+    m = hs2 != 0
+    assert float(m.float().mean()) > 0.5
+    err = float(((hs - hs2) * m).abs().max()) / (float(hs2.abs().max()) + 1e-20)
+    assert err <= 1e-5, f"block-start states: {err:.2e}"
