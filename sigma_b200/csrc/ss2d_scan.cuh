@@ -58,7 +58,6 @@ struct alignas(64) Ss2dParams {
   int I[4], O[4], rev[4];
   long long istride[4], ostride[4];   // y element strides of the inner / outer walk index
   int nsplit, tiles_per_split;
-  int npoly;   // d_state 16: state pairs per position whose exponential runs on the FMA pipe (0, 1, 2)
   int nst;     // TMA ring depth: as many LT-position stages as fit next to CTAS-1 other CTAs in shared memory
   int ablate;  // timing experiments, only in builds with -DSIGMA_SCAN_ABLATION (SIGMA_SCAN_ABLATE env):
                // 1 = no y store, 2 = no per-group prologue, 4 = no TMA reload
@@ -85,27 +84,6 @@ struct Ss2dThread {
   bool ok[CPT];
   int ablate;
 };
-
-// 2^x for a PAIR of x <= 0 on the FMA / ALU pipes instead of the SFU (the d_state-16 scans are MUFU-bound: 17 MUFU per channel
-// and position at 16 lanes per clock and SM): round to nearest integer with the 1.5·2^23 trick, degree-5 polynomial for 2^f on
-// [-0.5, 0.5] (max relative error 2.4e-7, the level of MUFU.EX2), exponent added into the bit pattern.  3 FADD2 + 5 FFMA2 on the
-// FMA pipe, 2 FMNMX + 2 LEA on the ALU pipe per pair.
-__device__ __forceinline__ f2 ex2_poly2(f2 x) {
-  x.x = fmaxf(x.x, -125.f); x.y = fmaxf(x.y, -125.f);          // keep the exponent field in range; 2^-125 ~ 0
-  const f2 magic = f2{12582912.f, 12582912.f};
-  unsigned long long t, r, f;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(pack2(x.x, x.y)), "l"(pack2(magic.x, magic.y)));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(t), "l"(pack2(magic.x, magic.y)));
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(f) : "l"(pack2(x.x, x.y)), "l"(r));
-  const f2 ff = unpack2(f);
-  f2 p = fma2(f2{0.0013390863314270973f, 0.0013390863314270973f}, ff, f2{0.009676031768321991f, 0.009676031768321991f});
-  p = fma2(p, ff, f2{0.055503569543361664f, 0.055503569543361664f});
-  p = fma2(p, ff, f2{0.2402210682630539f, 0.2402210682630539f});
-  p = fma2(p, ff, f2{0.6931471824645996f, 0.6931471824645996f});
-  p = fma2(p, ff, f2{1.0000001192092896f, 1.0000001192092896f});
-  const f2 tt = unpack2(t);
-  return f2{__int_as_float(__float_as_int(p.x) + (__float_as_int(tt.x) << 23)), __int_as_float(__float_as_int(p.y) + (__float_as_int(tt.y) << 23))};
-}
 
 // packed helpers on raw 64-bit register pairs (keep loop-invariant pairs paired: no MOVs to rebuild them)
 __device__ __forceinline__ unsigned long long fma2_raw(unsigned long long a, unsigned long long b, unsigned long long c) {
@@ -176,7 +154,7 @@ __device__ __forceinline__ void group_prologue(const Ss2dThread<N, CPT, RP> &t, 
 // channel lies beyond D walks a one-element sink instead (kernel prologue), so there is no branch around the store.
 // Per position B and C are read ONCE (2·N/4 broadcast LDS.128) and reused by the CPT channels of the thread;
 // per channel and state pair: FMUL2 (exp arguments), 2 x MUFU.EX2, FMUL2 (delta·u·B), FFMA2 (h), FFMA2 (C·h).
-template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL, bool SAVE = false, int NPOLY = 0>
+template <int N, int CPT, int RP, int G, bool WITH_Y, bool REV, bool FULL, bool SAVE = false>
 __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const float *rb, const float *rc, float *yq,
                                            int ystep, int ycstride, const float (&dl)[CPT][G],
                                            const float (&u)[CPT][G], int cnt, float *dq = nullptr) {
@@ -201,9 +179,7 @@ __device__ __forceinline__ void group_body(Ss2dThread<N, CPT, RP> &t, const floa
           for (int hp = 0; hp < 2; ++hp) {                                   // state pair (4·s4 + 2·hp, +1)
             const int s = 4 * s4 + 2 * hp;
             const f2 arg = mul2(f2{d, d}, f2{t.a2[c][s], t.a2[c][s + 1]});
-            // NPOLY of the N/2 state pairs take their exponentials from the FMA pipe (ex2_poly2), the rest from MUFU.EX2
-            const f2 a = (NPOLY > 0 && (s >> 1) % (N / 2 / (NPOLY > 0 ? NPOLY : 1)) == 0 && (s >> 1) / (N / 2 / (NPOLY > 0 ? NPOLY : 1)) < NPOLY)
-                             ? ex2_poly2(arg) : f2{ex2(arg.x), ex2(arg.y)};
+            const f2 a = f2{ex2(arg.x), ex2(arg.y)};
             const f2 bb = mul2(f2{du, du}, hp == 0 ? f2{bv.x, bv.y} : f2{bv.z, bv.w});
             const f2 hn = fma2(a, f2{t.h[c][s], t.h[c][s + 1]}, bb);
             t.h[c][s] = hn.x; t.h[c][s + 1] = hn.y;
@@ -255,7 +231,7 @@ struct Ss2dWalk {
 // The tile loop of one warp.  The software pipeline over groups of G positions runs ACROSS tiles: while the
 // recurrence of group g runs, delta'/u of group g+1 are computed — from the next tile's ring slot when g is the
 // last group of its tile — so no prologue is exposed at a tile boundary and none is computed twice.
-template <int N, int CPT, int RP, bool WITH_Y, bool REV, bool SAVE, int NPOLY, typename Request>
+template <int N, int CPT, int RP, bool WITH_Y, bool REV, bool SAVE, typename Request>
 __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2dWalk<N, CPT, RP> &w, Request &&request_tile) {
   constexpr int G = Ss2dCfg<N>::G, LT = Ss2dCfg<N>::LT;
   constexpr int Cp = 2 * N + RP;
@@ -340,10 +316,10 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
 #pragma unroll
             for (int i = 0; i < G; ++i) { dln[c][i] = dl[c][i] * 1.0001f; un[c][i] = u[c][i]; }
         }
-        group_body<N, CPT, RP, G, WITH_Y, REV, true, SAVE, NPOLY>(t, rb, rc, yp, w.ystep, ycs, dl, u, G, dp);
+        group_body<N, CPT, RP, G, WITH_Y, REV, true, SAVE>(t, rb, rc, yp, w.ystep, ycs, dl, u, G, dp);
       } else {
         group_prologue<N, CPT, RP, G>(t, px, pd, w.DT, dln, un);
-        group_body<N, CPT, RP, G, WITH_Y, REV, false, SAVE, NPOLY>(t, rb, rc, yp, w.ystep, ycs, dl, u, cnt, dp);
+        group_body<N, CPT, RP, G, WITH_Y, REV, false, SAVE>(t, rb, rc, yp, w.ystep, ycs, dl, u, cnt, dp);
       }
 #pragma unroll
       for (int c = 0; c < CPT; ++c)
@@ -366,7 +342,7 @@ __device__ __forceinline__ void walk_tiles(Ss2dThread<N, CPT, RP> &t, const Ss2d
   }
 }
 
-template <int N, int CPT, int RP, int MODE, int CTAS, bool SAVE = false, int NPOLY = 0>
+template <int N, int CPT, int RP, int MODE, int CTAS, bool SAVE = false>
 __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, CTAS) ss2d_scan_kernel(const __grid_constant__ Ss2dParams p) {
   static_assert(!SAVE || MODE != MODE_SUMMARY, "the summary pass has no final states to save");
   constexpr int LT = Ss2dCfg<N>::LT;
@@ -482,8 +458,8 @@ __global__ void __launch_bounds__(32 * Ss2dCfg<N>::MAXW, CTAS) ss2d_scan_kernel(
   w.t0 = t0; w.t1 = t1; w.TPO = TPO; w.ntiles = ntiles; w.I = I; w.nst = NST;
   w.cross = cross; w.rev = rev;
 
-  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true, SAVE, NPOLY>(t, w, request_tile);
-  else     walk_tiles<N, CPT, RP, WITH_Y, false, SAVE, NPOLY>(t, w, request_tile);
+  if (rev) walk_tiles<N, CPT, RP, WITH_Y, true, SAVE>(t, w, request_tile);
+  else     walk_tiles<N, CPT, RP, WITH_Y, false, SAVE>(t, w, request_tile);
 
   if (MODE == MODE_SUMMARY || SIGMA_ABL(p.ablate, 1)) {
 #pragma unroll

@@ -113,7 +113,6 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
   const int ndir = kind_dirs(kind);
   p.ndir = ndir;
   if (const char *e = getenv("SIGMA_SCAN_ABLATE")) p.ablate = atoi(e);
-  if (const char *e = getenv("SIGMA_SCAN_NPOLY")) p.npoly = std::max(0, std::min(2, atoi(e)));
   const int K = kind == SIGMA_DIRS_CROSS ? 1 : ndir;        // x_dbl rows per position
   const long long Lseq = kind == SIGMA_DIRS_SEQ2 ? 2LL * H * W : (long long)H * W;
   p.Lseq = Lseq;
