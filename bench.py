@@ -313,7 +313,7 @@ def measure_roofline(model, rgb, mx, reps=3):
     the calls (with their real inputs) are recorded during one eager forward, then each is replayed `reps` times
     back to back between two events after an L2 flush, so the interval contains kernel execution only (in the eager
     forward itself the host-side launch work of a call would sit between the events)."""
-    from sigma_b200 import fused
+    from sigma_b200 import _lib, fused
     calls = []
     orig = fused.ss2d_scan
 
@@ -344,10 +344,13 @@ def measure_roofline(model, rgb, mx, reps=3):
         b = scan_algo_bytes(c[0], c[7], c[8], c[9], c[10], c[11])
         tot_b += b
         tot_ms += ms
-        s_ = by_n.setdefault(c[11], [0, 0.0, 0])
+        s_ = by_n.setdefault(c[11], [0, 0.0, 0, 0])
         s_[0] += b
         s_[1] += ms
         s_[2] += 1
+        # exponentials of the call: (d_state + 1 softplus) per channel, position and direction -- the MUFU.EX2 work
+        ndir, Ls = {_lib.DIRS_CROSS4: (4, c[8] * c[9]), _lib.DIRS_SEQ2: (2, 2 * c[8] * c[9])}.get(c[0], (1, c[8] * c[9]))
+        s_[3] += c[7] * ndir * Ls * c[10] * (c[11] + 1)
         if os.environ.get("SIGMA_BENCH_DETAIL"):
             print(f"[scan call] kind={c[0]} batch={c[7]} HxW={c[8]}x{c[9]} D={c[10]} N={c[11]} R={c[12]}: {ms:.3f} ms "
                   f"{b / ms / 1e6:.0f} GB/s", file=sys.stderr)
@@ -739,6 +742,10 @@ def main():
                 "algorithmic_bytes_per_step": tot_b // passes, "scan_ms_per_step": round(tot_ms / passes, 3),
                 "by_dstate": {str(n): {"GBps": round(v[0] / (v[1] * 1e-3) / 1e9, 1), "ms_per_step": round(v[1] / passes, 3),
                                        "calls": v[2] // passes} for n, v in sorted(by_n.items())}}
+    # the d_state-16 scans are bound by the SFU, not by HBM: MUFU.EX2 issues 16 lanes per clock and SM (scripts/mufu_bench.cu)
+    sm_hz = ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+    roofline["mufu"] = {str(n): {"ex2_per_clk_per_sm": round(v[3] / (v[1] * 1e-3) / sm_hz / 148, 2), "peak": 16,
+                                 "frac": round(v[3] / (v[1] * 1e-3) / sm_hz / 148 / 16, 3)} for n, v in sorted(by_n.items())}
 
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
