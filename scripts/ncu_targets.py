@@ -1,7 +1,7 @@
 """Small drivers for `ncu --set full` captures of the round-2 kernels (one or two launches each).
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 2 -o gpurun_out/<name> python scripts/ncu_targets.py <which>
 which: opfwd (sigma_scan_fwd enc1 B=8 fp32) | opfwd_n4 (dec1) | opbwd (sigma_scan_bwd enc1 B=8) | gemm (stage-2 in_proj, tf32 and tf32x3) |
-       conv (CAB conv3x3 96->32 at 120x160, B=16)"""
+       conv (CAB conv3x3 96->32 at 120x160, B=16) | fusedbwd (FusedSS2DCore forward + backward, enc1 shape)"""
 import os
 import sys
 
@@ -53,5 +53,17 @@ elif which == "conv":
         torch.backends.cudnn.allow_tf32 = tf32
         for _ in range(2):
             fused.conv3x3(x, conv, gelu=True)
+elif which == "fusedbwd":      # the fused core's forward (SAVE build) + reverse sweep on the enc1 shape, 4 streams
+    from sigma_b200 import _lib
+    B, H, W, D, N, R = 4, 60, 80, 384, 16, 12
+    xc = torch.randn(B, H * W, D, device="cuda", generator=g).requires_grad_(True)
+    xpw = (torch.randn(4, R + 2 * N, D, device="cuda", generator=g) * D ** -0.5).requires_grad_(True)
+    dtw = ((torch.rand(4, D, R, device="cuda", generator=g) * 2 - 1) * R ** -0.5).requires_grad_(True)
+    dtb = (torch.rand(4, D, device="cuda", generator=g) * 4 - 5).requires_grad_(True)
+    Al = torch.log(torch.rand(4 * D, N, device="cuda", generator=g) * N + 0.5).requires_grad_(True)
+    Ds = torch.randn(4 * D, device="cuda", generator=g).requires_grad_(True)
+    for _ in range(2):
+        y = ops.FusedSS2DCore.apply(xc, xpw, dtw, dtb, Al, Ds, _lib.DIRS_CROSS4, H, W)
+        y.square().sum().backward()
 torch.cuda.synchronize()
 print("done", which)
