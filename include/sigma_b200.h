@@ -165,6 +165,12 @@ int sigma_ss2d_scan_bwd_saved(int kind, const float *xc, const float *xdbl, cons
 int sigma_layernorm_fwd(const float *x, const float *w, const float *b, float *y, int64_t rows,
                         int C, float eps, void *stream);
 
+/* Backward of sigma_layernorm_fwd (training path; the reference's autograd of nn.LayerNorm): dx (rows, C); dw (C) = sum over rows
+ * of dy·xhat, db (C) = sum over rows of dy — both zeroed inside, then accumulated.  mean / rstd are recomputed from x.
+ * C/4 must be one of {8, 16, 24, 32, 48, 64, 96, 128, 192, 256, 384} (every Sigma width up to 1536); else SIGMA_EUNSUPPORTED. */
+int sigma_layernorm_bwd(const float *x, const float *dy, const float *w, float *dx, float *dw, float *db, int64_t rows, int C,
+                        float eps, void *stream);
+
 /* PatchMerging2D front half (vmamba.py:619-633): y[b,i,j,:] = LayerNorm(cat(x[b,2i,2j], x[b,2i+1,2j], x[b,2i,2j+1],
  * x[b,2i+1,2j+1])) over 4C channels, zero rows beyond an odd H / W (F.pad).  x (batch,H,W,C) -> y (batch,⌈H/2⌉,⌈W/2⌉,4C);
  * the gather is index math inside the LayerNorm kernel (no concatenated tensor).  4C must be 32·k·{2,3,4,6,8,12,16}-shaped

@@ -39,6 +39,7 @@ SIGNATURES = {
     "sigma_ss2d_scan_bwd": (c_int, [c_int] + [c_void_p] * 14 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),
     "sigma_ss2d_scan_bwd_split": (c_int, [c_int] + [c_void_p] * 14 + [c_int] * 7 + [c_void_p, c_size_t, c_int, c_void_p]),
     "sigma_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
+    "sigma_layernorm_bwd": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_float, c_void_p]),
     "sigma_dwconv3x3_silu_fwd": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64] + [c_int] * 4 + [c_void_p]),
     "sigma_merge_norm_gate_fwd": (c_int, [c_void_p, c_int, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                           c_void_p, c_int64, c_int64, c_int64, c_int64, c_int, c_float, c_void_p]),

@@ -253,6 +253,8 @@ int sigma_scan_fwd_f32_split(const float *u, const float *delta, const float *A,
 // ---------------------------------------------------------------------------------------------
 namespace sigma {
 int row_norm_launch(const RowNormParams &p, cudaStream_t stream);
+int layernorm_bwd_launch(const float *x, const float *dy, const float *gamma, float *dx, float *dgamma, float *dbeta, long long rows,
+                         int D, float eps, cudaStream_t stream);
 int argmax_hist_launch(const float *logits, const void *labels, int label_bytes, unsigned long long *hist,
                        unsigned long long *counts, unsigned char *pred_out, int batch, int ncls, long long HW, cudaStream_t stream);
 int dwconv3x3_silu_launch(const float *x, long long x_row_stride, long long x_batch_stride, const float *w,
@@ -304,6 +306,14 @@ int sigma_layernorm_fwd(const float *x, const float *w, const float *b, float *y
   SIGMA_CHECK_ARG(al16(x) && al16(w) && al16(b) && al16(y), "sigma_layernorm_fwd: pointers must be 16-byte aligned");
   RowNormParams p{x, 0, 1, w, b, nullptr, 0, nullptr, y, rows, rows > 0 ? rows : 1, 0, 0, C, C, eps};
   return row_norm_launch(p, (cudaStream_t)stream);
+}
+
+int sigma_layernorm_bwd(const float *x, const float *dy, const float *w, float *dx, float *dw, float *db, int64_t rows, int C, float eps,
+                        void *stream) {
+  SIGMA_CHECK_ARG(x && dy && w && dx && dw && db, "sigma_layernorm_bwd: null pointer");
+  SIGMA_CHECK_ARG(C > 0 && C % 4 == 0 && rows >= 0, "sigma_layernorm_bwd: C=%d must be a positive multiple of 4", C);
+  SIGMA_CHECK_ARG(al16(x) && al16(dy) && al16(w) && al16(dx), "sigma_layernorm_bwd: pointers must be 16-byte aligned");
+  return layernorm_bwd_launch(x, dy, w, dx, dw, db, rows, C, eps, (cudaStream_t)stream);
 }
 
 int sigma_patch_merge_norm_fwd(const float *x, const float *w, const float *b, float *y, int batch, int H, int W, int C,

@@ -222,6 +222,133 @@ int row_norm_launch(const RowNormParams &p, cudaStream_t stream) {
   return SIGMA_OK;
 }
 
+// ---- LayerNorm backward (training path): dx, dgamma, dbeta of y = (x - mean)·rstd·gamma + beta over the last dim ----
+// Same lane layout as row_norm_fast_kernel (LPR lanes per row, V float4 per lane, 32/LPR rows per warp step); mean / rstd are
+// recomputed from x (x is read anyway), so the forward saves nothing.  A warp walks rows with a grid stride and keeps its lanes'
+// dgamma / dbeta columns in registers; they are reduced over the warp's sub-rows by shuffles and leave the warp as one
+// atomicAdd per column (torch's GammaBetaBackwardCUDAKernel spent 5.9 ms per Sigma-tiny training step on this reduction).
+template <int LPR, int V>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                             const float *__restrict__ gamma, float *__restrict__ dx,
+                                                             float *__restrict__ dgamma, float *__restrict__ dbeta, long long rows,
+                                                             int D, float eps) {
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / LPR, l = lane % LPR;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  const float invD = 1.f / (float)D;
+  constexpr bool GREG = V <= 6;        // wide rows re-read gamma through L1 instead of pinning 4·V more registers
+  float4 g[GREG ? V : 1], dg[V], db[V];
+  const float4 *gp = reinterpret_cast<const float4 *>(gamma) + l;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    if (GREG) g[v] = __ldg(gp + LPR * v);
+    dg[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    db[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long nsteps = (rows + RPW - 1) / RPW;
+  for (long long step = (long long)blockIdx.x * (blockDim.x >> 5) + warp; step < nsteps; step += wstride) {
+    const long long row_raw = step * RPW + sub;
+    const bool valid = row_raw < rows;
+    const long long row = valid ? row_raw : rows - 1;
+    const float4 *xr = reinterpret_cast<const float4 *>(x + row * D), *dr = reinterpret_cast<const float4 *>(dy + row * D);
+    float4 xv[V], dv[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { xv[v] = __ldcs(xr + l + LPR * v); dv[v] = __ldcs(dr + l + LPR * v); }
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) s += (xv[v].x + xv[v].y) + (xv[v].z + xv[v].w);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invD;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      xv[v].x -= mean; xv[v].y -= mean; xv[v].z -= mean; xv[v].w -= mean;
+      q += (xv[v].x * xv[v].x + xv[v].y * xv[v].y) + (xv[v].z * xv[v].z + xv[v].w * xv[v].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * invD + eps);
+    float s1 = 0.f, s2 = 0.f;          // Σ gamma·dy and Σ gamma·dy·xhat over the row
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      xv[v].x *= rstd; xv[v].y *= rstd; xv[v].z *= rstd; xv[v].w *= rstd;        // xhat
+      const float4 gv = GREG ? g[GREG ? v : 0] : __ldg(gp + LPR * v);
+      const float a0 = gv.x * dv[v].x, a1 = gv.y * dv[v].y, a2 = gv.z * dv[v].z, a3 = gv.w * dv[v].w;
+      s1 += (a0 + a1) + (a2 + a3);
+      s2 += (a0 * xv[v].x + a1 * xv[v].y) + (a2 * xv[v].z + a3 * xv[v].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float m1 = s1 * invD, m2 = s2 * invD;
+    float4 *outr = reinterpret_cast<float4 *>(dx + row * D);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const float4 gv = GREG ? g[GREG ? v : 0] : __ldg(gp + LPR * v);
+      float4 o;
+      o.x = rstd * (gv.x * dv[v].x - m1 - xv[v].x * m2);
+      o.y = rstd * (gv.y * dv[v].y - m1 - xv[v].y * m2);
+      o.z = rstd * (gv.z * dv[v].z - m1 - xv[v].z * m2);
+      o.w = rstd * (gv.w * dv[v].w - m1 - xv[v].w * m2);
+      if (valid) {
+        outr[l + LPR * v] = o;
+        dg[v].x = fmaf(dv[v].x, xv[v].x, dg[v].x); dg[v].y = fmaf(dv[v].y, xv[v].y, dg[v].y);
+        dg[v].z = fmaf(dv[v].z, xv[v].z, dg[v].z); dg[v].w = fmaf(dv[v].w, xv[v].w, dg[v].w);
+        db[v].x += dv[v].x; db[v].y += dv[v].y; db[v].z += dv[v].z; db[v].w += dv[v].w;
+      }
+    }
+  }
+  // the warp's sub-rows share columns: fold them onto sub-row 0
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      dg[v].x += __shfl_xor_sync(0xffffffffu, dg[v].x, o); dg[v].y += __shfl_xor_sync(0xffffffffu, dg[v].y, o);
+      dg[v].z += __shfl_xor_sync(0xffffffffu, dg[v].z, o); dg[v].w += __shfl_xor_sync(0xffffffffu, dg[v].w, o);
+      db[v].x += __shfl_xor_sync(0xffffffffu, db[v].x, o); db[v].y += __shfl_xor_sync(0xffffffffu, db[v].y, o);
+      db[v].z += __shfl_xor_sync(0xffffffffu, db[v].z, o); db[v].w += __shfl_xor_sync(0xffffffffu, db[v].w, o);
+    }
+  }
+  if (sub == 0) {                     // one red.global.add per column and warp (<= ~1M per call: the grid is sized for it)
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = 4 * (l + LPR * v);
+      atomicAdd(dgamma + c, dg[v].x); atomicAdd(dgamma + c + 1, dg[v].y); atomicAdd(dgamma + c + 2, dg[v].z); atomicAdd(dgamma + c + 3, dg[v].w);
+      atomicAdd(dbeta + c, db[v].x); atomicAdd(dbeta + c + 1, db[v].y); atomicAdd(dbeta + c + 2, db[v].z); atomicAdd(dbeta + c + 3, db[v].w);
+    }
+  }
+}
+
+template <int LPR, int V>
+static void layernorm_bwd_k(const float *x, const float *dy, const float *gamma, float *dx, float *dgamma, float *dbeta, long long rows,
+                            int D, float eps, cudaStream_t stream) {
+  const int warps = 8, rpw = 32 / LPR;
+  const long long nsteps = (rows + rpw - 1) / rpw;
+  // enough CTAs to fill the machine, few enough that the 2·D atomics per warp stay negligible (a warp walks >= 4 steps)
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(148 * 8, (nsteps + warps * 4 - 1) / (warps * 4)));
+  layernorm_bwd_kernel<LPR, V><<<grid, warps * 32, 0, stream>>>(x, dy, gamma, dx, dgamma, dbeta, rows, D, eps);
+}
+
+// dgamma / dbeta are zeroed here and accumulated into; false if D has no instantiation (the fast forward's D set)
+int layernorm_bwd_launch(const float *x, const float *dy, const float *gamma, float *dx, float *dgamma, float *dbeta, long long rows,
+                         int D, float eps, cudaStream_t stream) {
+  if (rows == 0) return SIGMA_OK;
+  if (D & 3) { set_error("layernorm_bwd: D=%d must be a multiple of 4", D); return SIGMA_EUNSUPPORTED; }
+  SIGMA_CHECK_CUDA(cudaMemsetAsync(dgamma, 0, (size_t)D * sizeof(float), stream));
+  SIGMA_CHECK_CUDA(cudaMemsetAsync(dbeta, 0, (size_t)D * sizeof(float), stream));
+  const int nvec = D >> 2;
+#define TRY(LPR, V) if (nvec == (LPR) * (V)) { layernorm_bwd_k<LPR, V>(x, dy, gamma, dx, dgamma, dbeta, rows, D, eps, stream); SIGMA_CHECK_LAUNCH(); return SIGMA_OK; }
+  TRY(8, 1) TRY(8, 2) TRY(8, 3) TRY(8, 4)
+  TRY(16, 3) TRY(16, 4)
+  TRY(32, 3) TRY(32, 4) TRY(32, 6) TRY(32, 8) TRY(32, 12)
+#undef TRY
+  set_error("layernorm_bwd: D=%d has no instantiation (D/4 = lanes-per-row x vectors in {8x1..4, 16x3..4, 32x3,4,6,8,12})", D);
+  return SIGMA_EUNSUPPORTED;
+}
+
 // ---- depthwise 3x3 + bias + SiLU, NHWC ----
 // CTA: 64 channels (16 float4 lanes) x 16 position-threads.  A thread produces DW_WB = 4 horizontally adjacent
 // outputs of its 4 channels from a 3 x 6 window held in registers (18 loads for 4 outputs instead of 36), the

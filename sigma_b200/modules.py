@@ -147,7 +147,7 @@ class PatchMerging2D(nn.Module):
         if (W % 2) or (H % 2):
             x = F.pad(x, (0, 0, 0, W % 2, 0, H % 2))
         x = torch.cat([x[..., 0::2, 0::2, :], x[..., 1::2, 0::2, :], x[..., 0::2, 1::2, :], x[..., 1::2, 1::2, :]], -1)
-        return self.reduction(self.norm(x))
+        return self.reduction(ops.layer_norm(self.norm, x))
 
 
 class SS2D(nn.Module):
@@ -203,7 +203,7 @@ class SS2D(nn.Module):
             xc = xi.permute(0, 2, 3, 1).reshape(B, H * W, self.d_inner)
             y = ops.FusedSS2DCore.apply(xc, self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias, self.A_logs, self.Ds,
                                         _lib_kinds()[0], H, W)
-            y = self.out_norm(y.view(B, H, W, self.d_inner)).to(x.dtype) * F.silu(z)
+            y = ops.layer_norm(self.out_norm, y.view(B, H, W, self.d_inner)).to(x.dtype) * F.silu(z)
         else:
             xi = self.act(self.conv2d(xi.permute(0, 3, 1, 2).contiguous()))
             y = self.forward_core(xi) * F.silu(z)
@@ -272,8 +272,8 @@ class ConMB_SS2D(nn.Module):
             c_e = self.act(self.conv2d_modalx(t_e)).permute(0, 2, 3, 1).reshape(B, L, D)
             ys = ops.FusedSS2DCore.apply(torch.cat([c_r, c_e], dim=1), self.x_proj_weight, self.dt_projs_weight, self.dt_projs_bias,
                                          self.A_logs, self.Ds, _lib_kinds()[1], H, W)                          # (B, 2L, D)
-            y_r = self.out_norm1(ys[:, :L].reshape(B, H, W, D)).to(x_rgb.dtype)
-            y_e = self.out_norm2(ys[:, L:].reshape(B, H, W, D)).to(x_e.dtype)
+            y_r = ops.layer_norm(self.out_norm1, ys[:, :L].reshape(B, H, W, D)).to(x_rgb.dtype)
+            y_e = ops.layer_norm(self.out_norm2, ys[:, L:].reshape(B, H, W, D)).to(x_e.dtype)
         else:
             y_r, y_e = self.forward_corev2_multimodal(self.act(self.conv2d(t_r)), self.act(self.conv2d_modalx(t_e)))
         g_r = self.fc1(t_r.mean(dim=(2, 3)))          # gates come from the PRE-conv projections (vmamba.py:1276-1279)
@@ -321,7 +321,7 @@ class Cross_Mamba_Attention_SSM(nn.Module):
                                     self.D_1.float(), self.dt_proj_1.bias.float(), True)
         y_e = ops.selective_scan_fn(x_e.transpose(1, 2), dt_e, -torch.exp(self.A_log_2.float()), B_e, C_r,
                                     self.D_2.float(), self.dt_proj_2.bias.float(), True)
-        return self.out_norm_1(y_r.transpose(1, 2)), self.out_norm_2(y_e.transpose(1, 2))
+        return ops.layer_norm(self.out_norm_1, y_r.transpose(1, 2)), ops.layer_norm(self.out_norm_2, y_e.transpose(1, 2))
 
 
 class CrossMambaFusion_SS2D_SSM(nn.Module):
@@ -415,9 +415,9 @@ class VSSBlock(nn.Module):
         if _fused_ok(input) and not self.mlp_branch:
             from . import fused
             return fused.vss_block(self, input)
-        x = input + self.drop_path(self.op(self.norm(input)))
+        x = input + self.drop_path(self.op(ops.layer_norm(self.norm, input)))
         if self.mlp_branch:
-            x = x + self.drop_path(self.mlp(self.norm2(x)))
+            x = x + self.drop_path(self.mlp(ops.layer_norm(self.norm2, x)))
         return x
 
     def forward(self, input):
@@ -479,8 +479,8 @@ class CVSSDecoderBlock(nn.Module):
         if _fused_ok(input):
             from . import fused
             return fused.cvss_decoder_block(self, input)
-        x = input * self.scale1 + self.drop_path(self.op(self.norm1(input)))
-        y = self.conv_blk(self.norm2(x).permute(0, 3, 1, 2).contiguous()) + (x * self.scale2).permute(0, 3, 1, 2)
+        x = input * self.scale1 + self.drop_path(self.op(ops.layer_norm(self.norm1, input)))
+        y = self.conv_blk(ops.layer_norm(self.norm2, x).permute(0, 3, 1, 2).contiguous()) + (x * self.scale2).permute(0, 3, 1, 2)
         return y.permute(0, 2, 3, 1).contiguous()
 
     def forward(self, input):
@@ -541,7 +541,7 @@ class ConcatMambaFusionBlock(nn.Module):
             return self.op(x_rgb, x_e, residual=x_rgb + x_e)     # the sum is added in the out_proj GEMM epilogue
         x = x_rgb + x_e + self.drop_path(self.op(x_rgb, x_e))
         if self.mlp_branch:
-            x = x + self.drop_path(self.mlp(self.norm2(x)))
+            x = x + self.drop_path(self.mlp(ops.layer_norm(self.norm2, x)))
         return x
 
     def forward(self, x_rgb, x_e):
@@ -769,7 +769,7 @@ class PatchExpand(nn.Module):
         x = self.expand(x)
         B, H, W, C = x.shape
         x = x.view(B, H, W, 2, 2, C // 4).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * H, 2 * W, C // 4)
-        return self.norm(x)
+        return ops.layer_norm(self.norm, x)
 
 
 class UpsampleExpand(nn.Module):
@@ -786,7 +786,7 @@ class UpsampleExpand(nn.Module):
         if _fused_ok(x) and isinstance(self.norm, nn.LayerNorm):
             from . import fused
             return fused.upsample_expand(self, x)
-        return self.norm(_bilinear_nhwc(self.linear(x), scale_factor=2))
+        return ops.layer_norm(self.norm, _bilinear_nhwc(self.linear(x), scale_factor=2))
 
 
 class FinalUpsample_X4(nn.Module):
@@ -803,7 +803,7 @@ class FinalUpsample_X4(nn.Module):
     def forward(self, x):
         x = _bilinear_nhwc(self.linear1(x), scale_factor=2)
         x = _bilinear_nhwc(self.linear2(x), scale_factor=2)
-        return self.norm(x)
+        return ops.layer_norm(self.norm, x)
 
 
 class Mamba_up(nn.Module):
@@ -877,7 +877,7 @@ class MambaDecoder(nn.Module):
             from . import fused
             x = fused.ln_nhwc(self.norm_up, y)
         else:
-            x = self.norm_up(y)
+            x = ops.layer_norm(self.norm_up, y)
         return (x, ups) if self.deep_supervision else x
 
     def up_x4(self, x, pz):

@@ -333,6 +333,48 @@ def fused_core_ok(xc, D, N):
     return FUSED_TRAINING and xc.is_cuda and N in (4, 16) and D % 64 == 0
 
 
+_LN_WIDTHS = {32, 64, 96, 128, 192, 256, 384, 512, 768, 1024, 1536}   # C with an instantiation of sigma_layernorm_bwd
+FUSED_LAYERNORM = True
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last dim under autograd: forward = sigma_layernorm_fwd, backward = sigma_layernorm_bwd (dx, dweight, dbias in
+    one pass over x and dy; nothing saved but x).  Numerics as F.layer_norm in fp32."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, weight, bias, eps):
+        x2 = x.contiguous().view(-1, x.shape[-1])
+        y = torch.empty_like(x2)
+        w, b = weight.contiguous(), bias.contiguous()
+        _lib.check(_lib.lib().sigma_layernorm_fwd(_ptr(x2), _ptr(w), _ptr(b), _ptr(y), x2.shape[0], x2.shape[1], float(eps), _stream()),
+                   "sigma_layernorm_fwd")
+        ctx.save_for_backward(x2, w)
+        ctx.eps = float(eps)
+        return y.view(x.shape)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        dy2 = dy.contiguous().float().view(-1, x2.shape[1])
+        dx = torch.empty_like(x2)
+        dw, db = torch.empty_like(w), torch.empty_like(w)
+        _lib.check(_lib.lib().sigma_layernorm_bwd(_ptr(x2), _ptr(dy2), _ptr(w), _ptr(dx), _ptr(dw), _ptr(db), x2.shape[0], x2.shape[1], ctx.eps,
+                                                 _stream()), "sigma_layernorm_bwd")
+        return dx.view(dy.shape), dw, db, None
+
+
+def layer_norm(norm, x):
+    """`norm(x)` for an nn.LayerNorm over the last dim: the library pair under autograd when the width has an instantiation, the module
+    itself otherwise (other widths, no affine parameters, CPU tensors are the caller's error elsewhere)."""
+    if (FUSED_LAYERNORM and x.is_cuda and torch.is_grad_enabled() and isinstance(norm, torch.nn.LayerNorm) and norm.elementwise_affine
+            and norm.bias is not None and len(norm.normalized_shape) == 1 and x.shape[-1] in _LN_WIDTHS
+            and (x.dtype == torch.float32 or torch.is_autocast_enabled())):
+        return LayerNormFn.apply(x, norm.weight, norm.bias, norm.eps)
+    return norm(x)
+
+
 FUSED_SAVE_STATES = True      # training forward keeps delta' and the block-start states, so the backward runs no state sweep
 
 
