@@ -76,13 +76,15 @@ static int dispatch_rp(const Ss2dParams &p, int nthreads, int ctas, cudaStream_t
 static int kind_dirs(int kind) { return kind == SIGMA_DIRS_CROSS4 ? 4 : (kind == SIGMA_DIRS_SEQ2 ? 2 : 1); }
 static int lt_for(int N) { return N >= 16 ? Ss2dCfg<16>::LT : Ss2dCfg<4>::LT; }
 
-// warps per CTA: the largest count <= maxw whose channel tile (32·cpt channels per warp) divides D;
-// ragged D falls back to enough warps to cover it with a partially filled last CTA (TMA zero-fills, stores are
-// predicated)
+// warps per CTA: a count <= maxw whose channel tile (32·cpt channels per warp) divides D, tried in the order 4, 2, 3, 1 —
+// 3-warp CTAs (D = 192: 2 x 96 channels) measured 10 % slower than 2-warp ones (3 x 64) on the four-direction scans at the
+// same 12 resident warps per SM, every other shape is fastest with 4 (profiles/r02_scan_warps_sweep.txt); ragged D falls
+// back to enough warps to cover it with a partially filled last CTA (TMA zero-fills, y goes to the sink)
 static int pick_warps(int D, int cpt, int maxw) {
   const int cpw = 32 * cpt;
-  for (int w = maxw; w >= 1; --w)
-    if (D % (cpw * w) == 0) return w;
+  const int order[4] = {4, 2, 3, 1};
+  for (int w : order)
+    if (w <= maxw && D % (cpw * w) == 0) return w;
   return std::max(1, std::min(maxw, (D + cpw - 1) / cpw));
 }
 
