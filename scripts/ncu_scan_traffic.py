@@ -16,7 +16,7 @@ ap.add_argument("--width", type=int, default=640)
 ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_scan_traffic.json"))
 a = ap.parse_args()
 lines = [ln for ln in open(a.csv) if ln.startswith('"')]
-rows = list(csv.DictReader(lines))
+rows = [r for r in csv.DictReader(lines) if "ss2d_scan_kernel" in r["Kernel Name"]]   # the CSV may hold every kernel of the step
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "usecond": 1e-6, "ms": 1e-3, "msecond": 1e-3, "nsecond": 1e-9, "second": 1}
 per = {}
 for r in rows:

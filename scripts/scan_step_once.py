@@ -21,8 +21,9 @@ ap.add_argument("--model", default="sigma_tiny")
 ap.add_argument("--height", type=int, default=480)
 ap.add_argument("--width", type=int, default=640)
 ap.add_argument("--num-classes", type=int, default=9)
+ap.add_argument("--precision", default="tf32x3", choices=["tf32x3", "tf32"], help="dense projections, as bench.py --precision")
 a = ap.parse_args()
-torch.backends.cuda.matmul.allow_tf32 = True
+torch.backends.cuda.matmul.allow_tf32 = a.precision == "tf32"
 torch.backends.cudnn.allow_tf32 = True
 torch.manual_seed(0)
 cfg = types.SimpleNamespace(backbone=a.model, decoder="MambaDecoder", num_classes=a.num_classes, image_height=a.height,
