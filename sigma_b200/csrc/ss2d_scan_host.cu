@@ -100,6 +100,33 @@ static int ss2d_pick_ctas(int N, int rp) {
   return (N == 16 && rp == 24) ? 4 : 3;
 }
 
+// Number of L-segments for a grid of `ctas` CTAs of `nw` warps walking `ntiles` tiles each.  Model: CTAs spread evenly over the
+// 148 SMs, the kernel lasts as long as its busiest SM; a warp's time per tile grows with the warps sharing its sub-partition
+// (MUFU / issue are shared: per-warp cost 1 : 1.5 : 2.25 for 1 : 2 : 3 warps); a segmented walk runs two passes (summary +
+// apply) and pays a fixed ring fill / parameter load per CTA (~2 tiles).  The three constants are a least-squares fit to the
+// B200 sweep of every Sigma call shape x {1, 2, 4, 8} images x 10 forced counts (profiles/r02_ss2d_split_sweep.txt): the
+// model's choices total 15.1 ms there, the per-row optimum 14.9 ms, the round-1 rule 19.9 ms.  Candidates within 3 % keep
+// the smaller count.
+static int ss2d_pick_segments(long long ctas, int nw, int ntiles, int N) {
+  (void)N;                                                    // d_state 4 and 16 fit the same constants
+  const double pf = 1.95;
+  const int cap_warps = 12;                                   // resident warps per SM (168 registers)
+  double best = 1e300;
+  int best_n = 1;
+  for (int n = 1; n <= std::min(kMaxSplit, ntiles); ++n) {
+    const int tps = (ntiles + n - 1) / n, ne = (ntiles + tps - 1) / tps;
+    if (ne != n) continue;
+    const long long per_sm = (ctas * ne + 147) / 148;         // CTAs on the busiest SM
+    const long long warps_sm = per_sm * nw;
+    const long long rounds = (warps_sm + cap_warps - 1) / cap_warps;
+    const long long w_smsp = (std::min<long long>(warps_sm, cap_warps) + 3) / 4;   // warps sharing a sub-partition
+    const double share = std::max(1.0, 0.75 * (double)w_smsp);
+    const double cost = (double)rounds * (tps + 2) * share * (ne > 1 ? pf : 1.0);
+    if (cost < best * 0.97) { best = cost; best_n = ne; }
+  }
+  return best_n;
+}
+
 size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N) {
   return (size_t)batch * kind_dirs(kind) * D * kMaxSplit * 2 * N * sizeof(float);
 }
@@ -153,17 +180,22 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
       return rc;
     max_tiles = std::max(max_tiles, p.O[k] * ((p.I[k] + LT - 1) / LT));
   }
-  // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY): a second pass over the data, so only when the unsplit grid
-  // leaves SM sub-partitions (148 x 4) without a warp.  Measured on B200 (profiles/r01_scan_variants.txt): with >= 1
-  // warp per sub-partition a single pass wins; below that, d_state <= 8 scans are best split "big" (to ~2 warps per
-  // sub-partition), d_state = 16 scans (each split repeats 16 exponentials per element) only up to ~1.
+  // L-segments (MODE_SUMMARY -> combine -> MODE_APPLY): a second pass over the data, so only when the unsplit grid leaves SM
+  // sub-partitions without a warp.  ss2d_pick_segments models the busiest SM (the old rule, "fill 592 warp slots", ignored
+  // wave quantisation: 312 CTAs of 2 warps put 6 warps on some SMs where 288 put 4 on every SM).  SIGMA_SCAN_SPLIT_RULE=old
+  // restores the round-1 rule for comparison.
   const long long ctas = (long long)((D + DT - 1) / DT) * ndir * batch;
   const long long warps = ctas * NW;
   const long long full = 148LL * 4;
   int nsplit = 1;
-  if (warps < full) {
-    const long long want = N >= 16 ? full : 2 * full;
-    nsplit = (int)std::min<long long>((want + warps - 1) / warps, kMaxSplit);
+  const char *rule = getenv("SIGMA_SCAN_SPLIT_RULE");
+  if (rule && rule[0] == 'o') {
+    if (warps < full) {
+      const long long want = N >= 16 ? full : 2 * full;
+      nsplit = (int)std::min<long long>((want + warps - 1) / warps, kMaxSplit);
+    }
+  } else if (warps < 3 * full) {
+    nsplit = ss2d_pick_segments(ctas, NW, max_tiles, N);
   }
   if (force_split > 0) nsplit = std::min(force_split, kMaxSplit);
   if (ws == nullptr || ws_bytes < ss2d_scan_workspace_bytes(kind, batch, D, N)) {
