@@ -378,11 +378,19 @@ static int make_tmap_2d_sw128(CUtensorMap *map, const float *base, long long row
 
 // BN is a multiple of 32 (the epilogue moves 32-column boxes); tiles that overhang N are clipped by TMA on both the
 // W load (zero fill) and the C store.
-static int pick_bn(int N) {
-  if (N <= 256) return ((N + 31) / 32) * 32;
-  for (int bn = 256; bn >= 128; bn -= 32)
-    if (N % bn == 0) return bn;
-  return 256;
+// With many row tiles (the throughput regime) this is the widest divisor of N (the A tile is re-read once per column tile);
+// with few (small batch: M of a few hundred rows) narrower tiles put more CTAs to work: cost = waves over the 148 persistent
+// CTAs x (bn + 128), the shared-memory bytes an MMA k-step reads for a 128 x bn tile.
+static int pick_bn(int N, long long m_tiles = 1 << 30) {
+  const int full = N <= 256 ? ((N + 31) / 32) * 32 : 256;
+  int best_bn = full;
+  long long best = -1;
+  for (int bn = full; bn >= 64; bn -= 32) {
+    const long long tiles = m_tiles * ((N + bn - 1) / bn);    // a last column tile that overhangs N is clipped by TMA, but costs a full tile
+    const long long cost = ((tiles + 147) / 148) * (bn + 128);
+    if (best < 0 || cost < best || (cost == best && N % bn == 0 && N % best_bn != 0)) { best = cost; best_bn = bn; }
+  }
+  return best_bn;
 }
 
 static int make_tmap_c(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld) {
@@ -438,7 +446,8 @@ int gemm_tf32_launch(const float *A, long long lda, const float *W, const float 
   p.x3_keep_hi = x3_keep_hi();
   p.bias = bias; p.residual = residual; p.rscale = rscale; p.C = C; p.ldr = ldr; p.ldc = ldc;
   p.M = (int)M; p.N = N; p.K = K;
-  p.BN = pick_bn(N);
+  p.BN = pick_bn(N, (M + GM_BM - 1) / GM_BM);
+  if (const char *e = getenv("SIGMA_GEMM_BN_RULE")) { if (e[0] == 'o') p.BN = pick_bn(N); }   // "old": ignore the row-tile count
   p.tmem_cols = 2 * (p.BN <= 16 ? 16 : p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256);   // two accumulator stages
   if (p.tmem_cols < 32) p.tmem_cols = 32;
   int rc;

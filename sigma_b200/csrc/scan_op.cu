@@ -276,13 +276,26 @@ __global__ void scan_combine_kernel(float *carry, long long nrows, int nsplit, i
   const long long row = idx / NP;
   const int n = (int)(idx - row * NP);
   float H = 0.f, Pc = 1.f;
-  for (int s = 0; s < nsplit; ++s) {
-    float *base = carry + (row * nsplit + s) * 2 * NP;
-    const float P = base[n], hl = base[NP + n];
-    base[n] = Pc;
-    base[NP + n] = H;
-    H = fmaf(P, H, hl);
-    Pc *= P;
+  float *base = carry + row * nsplit * 2 * NP + n;
+  // eight segments at a time: their 16 loads are issued together (the walk is in place, so a plain loop serialises on one
+  // L2 round trip per segment: 14 us for 24 segments at batch 1)
+  for (int s0 = 0; s0 < nsplit; s0 += 8) {
+    float P[8], hl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = s0 + j < nsplit;
+      P[j] = in ? base[(long long)(s0 + j) * 2 * NP] : 1.f;
+      hl[j] = in ? base[(long long)(s0 + j) * 2 * NP + NP] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (s0 + j < nsplit) {
+        base[(long long)(s0 + j) * 2 * NP] = Pc;
+        base[(long long)(s0 + j) * 2 * NP + NP] = H;
+        H = fmaf(P[j], H, hl[j]);
+        Pc *= P[j];
+      }
+    }
   }
 }
 

@@ -401,11 +401,22 @@ __global__ void scan_combine_rev_kernel(float *carry, long long nrows, int nspli
   const long long row = idx / NP;
   const int n = (int)(idx - row * NP);
   float Hc = 0.f;
-  for (int s = nsplit - 1; s >= 0; --s) {
-    float *base = carry + (row * nsplit + s) * 2 * NP;
-    const float P = base[n], gl = base[NP + n];
-    base[NP + n] = Hc;
-    Hc = fmaf(P, Hc, gl);
+  float *base = carry + row * nsplit * 2 * NP + n;
+  for (int s0 = nsplit - 1; s0 >= 0; s0 -= 8) {      // eight segments per round: their loads are issued together (see scan_combine_kernel)
+    float P[8], gl[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool in = s0 - j >= 0;
+      P[j] = in ? base[(long long)(s0 - j) * 2 * NP] : 1.f;
+      gl[j] = in ? base[(long long)(s0 - j) * 2 * NP + NP] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (s0 - j >= 0) {
+        base[(long long)(s0 - j) * 2 * NP + NP] = Hc;
+        Hc = fmaf(P[j], Hc, gl[j]);
+      }
+    }
   }
 }
 
