@@ -375,7 +375,9 @@ def pool_avgmax(t):
     """(B, H, W, C) channels-last -> mean and max over H·W, each (B, C)."""
     B, H, W, C = t.shape
     L = H * W
-    nslice = max(1, min(64, L // 256))
+    # slices of positions per image: enough CTAs (B·nslice >= 2 per SM) that a single image does not walk its map with a handful
+    # of them (B = 1, 30x40 map: 4 CTAs took 74 us), at least 32 positions per slice
+    nslice = max(1, min(64, L // 32, max(L // 256, -(-296 // B))))
     part = torch.empty((B, nslice, 2, C), dtype=torch.float32, device=t.device)
     _lib.check(_lib.lib().sigma_pool_avgmax_partial_fwd(_p(t), _p(part), B, L, C, nslice, _stream()), "sigma_pool_avgmax_partial_fwd")
     return part[:, :, 0].sum(1) / L, part[:, :, 1].amax(1)
