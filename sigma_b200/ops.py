@@ -395,8 +395,10 @@ def _call_ss2d_bwd(args, saved=False):
 class FusedSS2DCore(torch.autograd.Function):
     """cross_selective_scan (vmamba.py:165-226, kind CROSS4) / cross_selective_scan_multimodal_k2 (:369-430, kind SEQ2) without
     out_norm, on channels-last activations:  xc (B, Lseq, D) -> y (B, Lseq, D) = sum over directions of the scan outputs, each at
-    the position it belongs to (CrossMerge).  Forward = the inference kernels (x_proj GEMM + sigma_ss2d_scan_fwd); backward =
-    sigma_ss2d_scan_bwd (no CrossScan / delta / CrossMerge tensors) + the x_proj / dt_proj weight-gradient GEMMs."""
+    the position it belongs to (CrossMerge).  Forward = the inference kernels (x_proj GEMM + the fused scan) in their state-saving
+    build (sigma_ss2d_scan_fwd_save: also keeps delta' and the scan state entering every 16-position block); backward =
+    sigma_ss2d_scan_bwd_saved (one reverse sweep; no CrossScan / CrossMerge tensors) + the x_proj / dt_proj weight-gradient GEMMs.
+    With FUSED_SAVE_STATES = False the plain forward runs and sigma_ss2d_scan_bwd recomputes both in a state sweep."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
