@@ -34,6 +34,8 @@ SIGNATURES = {
     "sigma_ss2d_scan_fwd_split": (c_int, [c_int] + [c_void_p] * 7 + [c_int] * 7 + [c_void_p, c_size_t, c_int, c_void_p]),
     "sigma_ss2d_scan_bwd_workspace_bytes": (c_size_t, [c_int] * 6),
     "sigma_ss2d_scan_hs_bytes": (c_size_t, [c_int] * 6),
+    "sigma_test_pick_segments": (c_int, [c_int64, c_int, c_int, c_int]),
+    "sigma_test_pick_bn": (c_int, [c_int, c_int64]),
     "sigma_ss2d_scan_fwd_save": (c_int, [c_int] + [c_void_p] * 9 + [c_int] * 7 + [c_void_p, c_size_t, c_int, c_void_p]),
     "sigma_ss2d_scan_bwd_saved": (c_int, [c_int] + [c_void_p] * 15 + [c_int] * 7 + [c_void_p, c_size_t, c_int, c_void_p]),
     "sigma_ss2d_scan_bwd": (c_int, [c_int] + [c_void_p] * 14 + [c_int] * 7 + [c_void_p, c_size_t, c_void_p]),

@@ -265,6 +265,8 @@ int ss2d_scan_fwd(int kind, const float *xc, const float *xdbl, const float *dtw
                   const float *Ds, float *y, int batch, int H, int W, int D, int N, int R, int Cp, void *ws,
                   size_t ws_bytes, int force_split, cudaStream_t stream, float *dsave = nullptr, float *hsave = nullptr);
 size_t ss2d_scan_hs_bytes(int kind, int batch, int H, int W, int D, int N);
+int ss2d_pick_segments_hook(long long ctas, int nw, int ntiles, int N);
+int gemm_pick_bn_hook(int N, long long m_tiles);
 size_t ss2d_scan_bwd_workspace_bytes(int kind, int batch, int H, int W, int D, int N);
 int ss2d_scan_bwd(int kind, const float *xc, const float *xdbl, const float *dtw, const float *dtb, const float *A, const float *Ds,
                   const float *dy, float *delta, float *dxc, float *ddelta, float *dxdbl, float *dA, float *dDs, float *ddtb, int batch,
@@ -410,6 +412,10 @@ int sigma_ss2d_scan_fwd_split(int kind, const float *xc, const float *xdbl, cons
   return ss2d_scan_fwd(kind, xc, xdbl, dtw, dtb, A, Ds, y, batch, H, W, D, N, R, Cp, workspace, workspace_bytes, nsplit,
                        (cudaStream_t)stream);
 }
+
+// test hooks (host logic only, no CUDA call): the launch heuristics, so that CPU tests can hold them to the recorded sweeps
+int sigma_test_pick_segments(long long ctas, int warps_per_cta, int ntiles, int N) { return ss2d_pick_segments_hook(ctas, warps_per_cta, ntiles, N); }
+int sigma_test_pick_bn(int N, long long m_tiles) { return gemm_pick_bn_hook(N, m_tiles); }
 
 // training forward: the forward plus what the fused backward needs (delta' slabs, block-start states)
 size_t sigma_ss2d_scan_hs_bytes(int kind, int batch, int H, int W, int D, int N) {

@@ -393,6 +393,8 @@ static int pick_bn(int N, long long m_tiles = 1 << 30) {
   return best_bn;
 }
 
+int gemm_pick_bn_hook(int N, long long m_tiles) { return pick_bn(N, m_tiles); }   // api.cu test hook
+
 static int make_tmap_c(CUtensorMap *map, const float *base, long long rows, long long cols, long long ld) {
   EncodeTiledFn2 fn = (EncodeTiledFn2)get_tensor_map_encoder();
   if (!fn) return SIGMA_ECUDA;

@@ -127,6 +127,8 @@ static int ss2d_pick_segments(long long ctas, int nw, int ntiles, int N) {
   return best_n;
 }
 
+int ss2d_pick_segments_hook(long long ctas, int nw, int ntiles, int N) { return ss2d_pick_segments(ctas, nw, ntiles, N); }   // api.cu test hook
+
 size_t ss2d_scan_workspace_bytes(int kind, int batch, int D, int N) {
   return (size_t)batch * kind_dirs(kind) * D * kMaxSplit * 2 * N * sizeof(float);
 }
